@@ -1,0 +1,83 @@
+"""CPU, differential: the C restatement against the compiled reference binaries in
+oracle/_ref on seeded random inputs (skipped where oracle/_ref was not built)."""
+import os
+
+import numpy as np
+import pytest
+
+from pangaea_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return oracle
+
+
+@pytest.mark.parametrize("seed,style,mode", [(1, "10x", "i"), (2, "stlfr", "p"), (3, "10x", "p"), (4, "stlfr", "i")])
+def test_random_inputs(ref, tmp_path, seed, style, mode):
+    O = ref
+    rng = np.random.default_rng(seed)
+    data = synth.generate(n_barcodes=int(rng.integers(3, 30)), mean_pairs=int(rng.integers(2, 25)),
+                          read_len=int(rng.integers(20, 160)), n_genomes=2, genome_len=20_000, frag_len=4_000,
+                          seed=seed, unbarcoded_pairs=int(rng.integers(0, 6)), n_rate=0.003, lower_rate=0.002)
+    if mode == "i":
+        p1, p2 = synth.write_interleaved(str(tmp_path / "i.fq"), data, style=style), None
+        kw = dict(interleaved=p1)
+    else:
+        p1, p2 = synth.write_paired(str(tmp_path / "1.fq"), str(tmp_path / "2.fq"), data, style=style)
+        kw = dict(reads1=p1, reads2=p2)
+    k, ws, vs = int(rng.integers(5, 20)), int(rng.integers(1, 4)), int(rng.integers(3, 50))
+    mlen = int(rng.choice([0, 500, 2000]))
+    t = O.count_fastq([p for p in (p1, p2) if p], k)
+    dump = str(tmp_path / "d.dump")
+    t.write_dump(dump, k)
+    labels, abd = O.abundance(p1, p2, t, k, mlen, vs, ws)
+    rl, rabd = O.ref_count_kmer(str(tmp_path / "a.gz"), dump, k=k, mlen=mlen, vs=vs, ws=ws, **kw)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(abd, rabd)
+    labels, tnf = O.tnf(p1, p2, 4, mlen)
+    rl, rtnf = O.ref_count_tnf(str(tmp_path / "t.gz"), k=4, mlen=mlen, **kw)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(tnf, rtnf)
+
+
+def test_kat6_thread_count_does_not_change_output(ref, tmp_path):
+    data = synth.generate(n_barcodes=30, mean_pairs=10, read_len=60, seed=9)
+    fq = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    a = ref.ref_count_tnf(str(tmp_path / "t1.gz"), interleaved=fq, mlen=0, threads=1)
+    b = ref.ref_count_tnf(str(tmp_path / "t8.gz"), interleaved=fq, mlen=0, threads=8)
+    assert list(a[0]) == list(b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_kat7_min_length_counts_separators(ref, tmp_path):
+    """Σ(len+1) <= -l drops the row (count_tnf.cpp:81): 3 pairs of 2x30 -> 186."""
+    with open(tmp_path / "i.fq", "wb") as f:
+        for i, bc in enumerate([b"AA"] + [b"AA"] * 3 + [b"CC"]):
+            for _ in range(2):
+                f.write(b"@r%d BX:Z:%s-1\n%s\n+\n%s\n" % (i, bc, b"ACGTTGCAAC" * 3, b"I" * 30))
+    fq = str(tmp_path / "i.fq")
+    # cloud AA holds pairs 1..4 (pair 0 is lost to the quirk, pair 4 = first CC pair) = 4 * 62 = 248
+    for mlen, want in ((247, ["AA"]), (248, [])):
+        labels, _ = ref.ref_count_tnf(str(tmp_path / f"t{mlen}.gz"), interleaved=fq, mlen=mlen)
+        assert list(labels) == want
+        assert list(ref.tnf(fq, None, 4, mlen)[0]) == want
+
+
+def test_kat5_csv_precision_loss_is_text_only(ref, tmp_path):
+    """Tallies >= 1e6 print as 1.xxxxxe+06 (ostream precision 6, count_tnf.cpp:204);
+    the oracle keeps exact integers, the text rounds them."""
+    n_pairs = 2200
+    with open(tmp_path / "i.fq", "wb") as f:
+        for i in range(n_pairs + 2):
+            bc = b"AA" if i <= n_pairs else b"CC"
+            for _ in range(2):
+                f.write(b"@r%d BX:Z:%s-1\n%s\n+\n%s\n" % (i, bc, b"A" * 250, b"I" * 250))
+    fq = str(tmp_path / "i.fq")
+    labels, tnf = ref.tnf(fq, None, 4, 0)
+    exact = int(tnf[0, 0])
+    assert exact == (n_pairs + 1) * 2 * 247 and exact >= 1_000_000
+    rl, rt = ref.ref_count_tnf(str(tmp_path / "t.gz"), interleaved=fq, mlen=0)
+    assert rt.dtype == np.float64  # pandas sees scientific notation
+    assert rt[0, 0] == float("%.6g" % exact) and rt[0, 0] != exact
