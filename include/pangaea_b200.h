@@ -1,0 +1,185 @@
+/*
+ * pangaea_b200.h - C-ABI of the B200-native read-cloud featurization path.
+ *
+ * This is the drop-in boundary for Pangaea's step 1 ("feature extraction").  The
+ * reference has no FFI on this path: src/feature.py drives three subprocesses
+ * (jellyfish, bin/count_kmer, bin/count_tnf) and reads their gz-CSV files back with
+ * pandas.  The entry points below are what a maintainer binds (ctypes stub in
+ * INTEGRATION.md) in place of those subprocess calls; each one names the reference
+ * interface it replaces.  Citations are relative to /root/reference/.
+ *
+ * Conventions
+ *   - plain C types only; every function returns PG_OK (0) or a negative pg_status
+ *     and leaves a message for pg_last_error();
+ *   - a pg_ctx owns one CUDA device, one stream, the k-mer count table and all
+ *     scratch; it has no global mutable state (the reference's `read_type` global,
+ *     count_kmer.cpp:24, lives in the parser object instead) and may be driven
+ *     from any one thread at a time with the GIL released;
+ *   - there is NO CPU fallback: without a CUDA device pg_create fails.
+ *
+ * Read batches.  A batch is the sequence lines of consecutive FASTQ records, each
+ * followed by ONE separator byte (any non-ACGT byte; the parser uses '\n'), i.e.
+ * exactly the string the reference builds per cloud with `reads_seq += line + "N"`
+ * (count_kmer.cpp:247-250, :199).  read_off[r+1]-read_off[r] = len(read r)+1, so
+ * the reference's min-length rule `reads_seq.size() <= mlen` (count_kmer.cpp:62) is
+ * a difference of offsets.  read_flag[r] carries the grouping decisions the
+ * reference's main() loop takes while streaming (count_kmer.cpp:181-282):
+ *   PG_READ_CHANGE  the barcode compared unequal to last_barcode when this read
+ *                   was appended: the cloud is flushed AFTER this read (set on the
+ *                   R2 read of the triggering pair - the reference's off-by-one);
+ *   PG_READ_NOFEAT  read is counted (jellyfish sees every record) but belongs to
+ *                   no cloud (R1/R2 name or barcode mismatch, count_kmer.cpp:195).
+ * Cloud g = number of PG_READ_CHANGE flags on earlier reads; its label is the
+ * barcode of the pair that carried the g-th flag ("" for g = 0).  group_keep[g]
+ * is 0 when that label is empty (count_kmer.cpp:62 `barcode.empty()`).
+ */
+#ifndef PANGAEA_B200_H
+#define PANGAEA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pg_status {
+    PG_OK = 0,
+    PG_ERR_INVALID = -1,  /* bad argument */
+    PG_ERR_CUDA = -2,     /* CUDA runtime error (no device, OOM, launch failure) */
+    PG_ERR_CAPACITY = -3, /* hash table full - raise table_capacity */
+    PG_ERR_IO = -4,       /* file could not be opened / read */
+    PG_ERR_STATE = -5     /* call out of order (e.g. featurize before count) */
+} pg_status;
+
+enum { PG_READ_CHANGE = 1, PG_READ_NOFEAT = 2 };
+enum { PG_TABLE_AUTO = 0, PG_TABLE_DENSE = 1, PG_TABLE_HASH = 2 };
+
+/* Replaces the CLI flags of count_kmer (count_kmer.cpp:112-123) / count_tnf
+ * (count_tnf.cpp:117-125) as passed by feature.py:107-109,131-133, and the
+ * jellyfish flags at feature.py:76-94. */
+typedef struct pg_params {
+    int32_t device;          /* CUDA ordinal */
+    int32_t k;               /* -k, 15: k-mer size of the abundance feature, 1..31 */
+    int32_t tnf_k;           /* count_tnf -k, 4: 1..6 */
+    int32_t window_size;     /* -w, 10: abundance bin width (count / w) */
+    int32_t vector_size;     /* -v, 400: abundance bins */
+    int64_t min_length;      /* -l, 2000: clouds with sum(len+1) <= this are dropped */
+    int32_t min_qual_char;   /* jellyfish --min-qual-char (0 = off; '?' in the -1/-2 branch) */
+    int32_t table_mode;      /* PG_TABLE_*: dense direct-addressed (k <= 16) or open-addressing hash */
+    uint64_t table_capacity; /* hash slots (power of two; 0 = sized from the first batch) */
+} pg_params;
+
+typedef struct pg_reads {
+    const uint8_t* seq;       /* n_bytes: read bytes + 1 separator per read */
+    const uint8_t* qual;      /* same layout, or NULL (only read when min_qual_char != 0) */
+    const int64_t* read_off;  /* n_reads + 1 offsets into seq, read_off[0] = 0 */
+    const uint8_t* read_flag; /* n_reads: PG_READ_* bits */
+    int64_t n_reads;
+    int64_t n_bytes;          /* = read_off[n_reads] */
+} pg_reads;
+
+typedef struct pg_ctx pg_ctx;
+typedef struct pg_batch pg_batch;       /* a read batch resident in HBM (ASCII + 2-bit packed) */
+typedef struct pg_features pg_features; /* per-cloud matrices resident in HBM */
+
+/* ---- lifetime -------------------------------------------------------------- */
+void pg_default_params(pg_params* p);
+int pg_create(const pg_params* p, pg_ctx** out);
+void pg_destroy(pg_ctx* ctx);
+/* message of the last failure on ctx (ctx may be NULL: failure of pg_create / parser) */
+const char* pg_last_error(const pg_ctx* ctx);
+int pg_device_count(void);
+/* tnf_k -> number of canonical columns (136 for 4); count_tnf.cpp:138-164 */
+int pg_tnf_dim(int tnf_k);
+int pg_synchronize(pg_ctx* ctx);
+/* the cudaStream_t every launch of this ctx goes to (for CUDA-event timing by the caller) */
+void* pg_stream(pg_ctx* ctx);
+
+/* ---- batches --------------------------------------------------------------- */
+/* copy a host batch to HBM (async on the ctx stream; pinned memory overlaps) and 2-bit pack it */
+int pg_batch_upload(pg_ctx* ctx, const pg_reads* host, pg_batch** out);
+/* adopt device pointers without copying (pointers must stay valid; seq 16-byte aligned) and pack */
+int pg_batch_adopt(pg_ctx* ctx, const pg_reads* dev, pg_batch** out);
+void pg_batch_free(pg_ctx* ctx, pg_batch* b);
+int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE flags */
+
+/* ---- step 1a: global canonical k-mer counts --------------------------------- */
+/* replaces `jellyfish count -C -m k` (+ `dump`), feature.py:76-94,103, and the dump
+ * loader count_kmer.cpp:139-170 (the table simply stays in HBM).  Adds the batch. */
+int pg_count(pg_ctx* ctx, pg_batch* b);
+int pg_table_clear(pg_ctx* ctx);
+/* kmer2frequency[key] = count (count_kmer.cpp:166): assignment, keys in the reference's
+ * canonical form or not (re-canonicalised).  count 0 is stored as "absent". */
+int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* counts, int64_t n);
+int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* counts_out, int64_t n);
+/* number of distinct k-mers; then export (key = reference canonical form, ascending) */
+int pg_table_size(pg_ctx* ctx, int64_t* n_distinct);
+int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts_out, int64_t cap, int64_t* n_out);
+/* dense mode only: device pointer and entry count of the u32 counter array, so a
+ * data-parallel caller can sum tables across ranks (ncclAllReduce) - SURVEY §8e */
+int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entries);
+
+/* ---- step 1b: per-cloud abundance histogram + TNF --------------------------- */
+/* replaces bin/count_kmer (countKmer, count_kmer.cpp:55-108) and bin/count_tnf
+ * (countKmer, count_tnf.cpp:78-113) in one pass over the packed bases.  group_keep:
+ * n_groups bytes (host memory), see header comment.  Rows come out in file order. */
+int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out);
+void pg_features_free(pg_ctx* ctx, pg_features* f);
+int64_t pg_features_rows(const pg_features* f);
+int32_t pg_features_abd_dim(const pg_features* f);
+int32_t pg_features_tnf_dim(const pg_features* f);
+/* cloud index (into the caller's label list) of every emitted row */
+int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t* groups_out);
+/* raw tallies, int32 row-major [rows, dim] - what the CSV files held as text */
+int pg_features_copy_raw(pg_ctx* ctx, const pg_features* f, int32_t* abd_out, int32_t* tnf_out);
+
+/* ---- step 2 prologue: Data.__init__ (src/data.py:16-21) --------------------- */
+/* L1-normalise both matrices (fp64 divide, fp32 store) and weights = max(abd row)^2 (fp64) */
+int pg_normalize(pg_ctx* ctx, pg_features* f);
+int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, float* abd_out, float* tnf_out, double* weights_out);
+
+/* wrap caller-provided raw tallies (host memory, row-major) so pg_normalize can run on them:
+ * the `Data(barcodes, abd, tnf)` entry when the matrices come from load_features() */
+int pg_features_from_raw(pg_ctx* ctx, const uint32_t* abd, const uint32_t* tnf, int64_t rows, int32_t abd_dim, int32_t tnf_dim, pg_features** out);
+
+/* zero-copy hand-off: which = 0 abd_raw(i32) 1 tnf_raw(i32) 2 abd(f32) 3 tnf(f32) 4 weights(f64).
+ * Returns a DLManagedTensor* (DLPack v0.8 layout) whose deleter releases a reference
+ * on the feature set; wrap it in a PyCapsule named "dltensor". */
+void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which);
+/* raw device pointer of the same buffers (valid until pg_features_free) */
+void* pg_features_device_ptr(const pg_features* f, int which);
+
+/* ---- whole path with HOST buffers (the e2e call) ---------------------------- */
+/* upload + count + featurize + normalize; the table is cleared first. */
+int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint8_t* group_keep, int64_t n_groups, pg_features** out);
+
+/* ---- host FASTQ reader (replaces the getline loops, count_kmer.cpp:181-282,
+ *      and getBarcode, count_kmer.cpp:25-53) ------------------------------------ */
+typedef struct pg_fastq pg_fastq;
+/* path2 == NULL: interleaved (-i), else paired (-1/-2).  Plain text or gzip. */
+int pg_fastq_parse(const char* path1, const char* path2, int want_qual, pg_fastq** out);
+void pg_fastq_free(pg_fastq* fq);
+void pg_fastq_reads(const pg_fastq* fq, pg_reads* out);      /* host pointers owned by fq */
+int64_t pg_fastq_n_groups(const pg_fastq* fq);
+const uint8_t* pg_fastq_group_keep(const pg_fastq* fq);       /* n_groups bytes */
+const char* pg_fastq_group_label(const pg_fastq* fq, int64_t g);
+
+/* ---- synthetic reads on device (bench input) --------------------- */
+/* fills DEVICE buffers shaped like a pg_reads batch: n_pairs pairs of 2 x read_len,
+ * (read_len + 1) bytes per read.  d_bc_start[n_barcodes + 1] = first pair of every
+ * barcode, d_bc_genome[n_barcodes] = its genome (both device memory). */
+int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
+                      const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
+                      double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag);
+
+/* ---- instrumentation -------------------------------------------------------- */
+/* device time (ms, CUDA events on the ctx stream) and launch count of the kernels run
+ * since the last reset: which = 0 pack, 1 count, 2 group, 3 featurize, 4 normalize, 5 all */
+int pg_timing_reset(pg_ctx* ctx);
+int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANGAEA_B200_H */

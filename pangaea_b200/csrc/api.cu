@@ -1,0 +1,898 @@
+// api.cu - C-ABI (include/pangaea_b200.h) over the sm_100a kernels.
+// Host orchestration only: allocation, launches, read-backs.  No CPU compute path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/pangaea_b200.h"
+#include "count.cuh"
+#include "featurize.cuh"
+#include "kmer.cuh"
+#include "normalize.cuh"
+#include "pack.cuh"
+#include "scan.cuh"
+#include "synth.cuh"
+#include "table.cuh"
+
+using namespace pg;
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5 };
+
+struct pg_ctx {
+    pg_params p;
+    int td = 0;
+    int mode = kDense;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // table
+    uint32_t* counts = nullptr;
+    unsigned long long* keys = nullptr;
+    uint64_t n_slots = 0;
+    uint32_t* d_overflow = nullptr;
+    bool counted = false;
+    // TNF look-up table
+    uint16_t* d_lut = nullptr;
+    // pinned read-back scratch
+    int64_t* h_pin = nullptr;
+    int64_t* d_scalar = nullptr; // 8 x int64 device scalars
+    std::string err;
+    // timing
+    struct Span { int which; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    int64_t launches[5] = { 0, 0, 0, 0, 0 };
+};
+
+struct pg_batch {
+    uint8_t *seq = nullptr, *qual = nullptr, *read_flag = nullptr;
+    int64_t* read_off = nullptr;
+    bool owns = false;
+    int64_t n_reads = 0, n_bytes = 0, n_words = 0;
+    uint64_t* codes = nullptr;
+    uint32_t *maskF = nullptr, *maskC = nullptr;
+    int64_t n_groups = -1; // counted on device, lazily
+};
+
+struct pg_features {
+    int refs = 1;
+    int device = 0;
+    int64_t rows = 0;
+    int32_t vs = 0, td = 0;
+    uint32_t *abd_raw = nullptr, *tnf_raw = nullptr;
+    float *abd = nullptr, *tnf = nullptr;
+    double* weights = nullptr;
+    int32_t* group_of_row = nullptr;
+    bool normalized = false;
+};
+
+static thread_local std::string g_err;
+
+static int fail(pg_ctx* c, int code, const std::string& msg)
+{
+    g_err = msg;
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct Timed { // CUDA-event span on the ctx stream around the launches of one stage
+    pg_ctx* c; int which; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(pg_ctx* c)
+    {
+        if (!c->pool.empty()) { cudaEvent_t e = c->pool.back(); c->pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    Timed(pg_ctx* c_, int w, int n_launches) : c(c_), which(w)
+    {
+        a = get(c); b = get(c);
+        cudaEventRecord(a, c->stream);
+        c->launches[w] += n_launches;
+    }
+    ~Timed()
+    {
+        cudaEventRecord(b, c->stream);
+        c->spans.push_back({ which, a, b });
+        if (c->spans.size() > 4096) { // nobody is reading the spans: recycle the oldest
+            c->pool.push_back(c->spans.front().a); c->pool.push_back(c->spans.front().b);
+            c->spans.erase(c->spans.begin());
+        }
+    }
+};
+
+static inline int grid_for(int64_t n, int threads, int cap)
+{
+    int64_t g = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+template <class T>
+static cudaError_t dmalloc(pg_ctx* ctx, T** p, size_t n)
+{
+    return cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+}
+static void dfree(pg_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+// ---------------------------------------------------------------------------
+// TNF column table (count_tnf.cpp:54-76,138-164): column = rank of the canonical code
+// ---------------------------------------------------------------------------
+static int build_tnf_lut(int tk, std::vector<uint16_t>* lut)
+{
+    const int n = 1 << (2 * tk);
+    std::vector<int> col_of_code(n, -1);
+    int cols = 0;
+    for (int v = 0; v < n; ++v)
+        if (canonical_of_fwd((uint64_t)v, tk) == (uint64_t)v) col_of_code[v] = cols++;
+    if (lut) {
+        lut->resize(n);
+        for (int w = 0; w < n; ++w) // w = LSB-first window as the kernels see it
+            (*lut)[w] = (uint16_t)col_of_code[canonical_of_window((uint64_t)w, tk)];
+    }
+    return cols;
+}
+
+extern "C" int pg_tnf_dim(int tnf_k) { return (tnf_k < 1 || tnf_k > 6) ? -1 : build_tnf_lut(tnf_k, nullptr); }
+
+extern "C" int pg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void pg_default_params(pg_params* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->device = 0;
+    p->k = 15;            // pangaea.py:140
+    p->tnf_k = 4;         // pangaea.py:139
+    p->window_size = 10;  // pangaea.py:141
+    p->vector_size = 400; // pangaea.py:142
+    p->min_length = 2000; // pangaea.py:138
+    p->min_qual_char = 0;
+    p->table_mode = PG_TABLE_AUTO;
+    p->table_capacity = 0;
+}
+
+extern "C" const char* pg_last_error(const pg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+static TableView view(pg_ctx* c)
+{
+    TableView t;
+    t.counts = c->counts; t.keys = c->keys; t.capacity_mask = c->n_slots ? c->n_slots - 1 : 0;
+    t.overflow = c->d_overflow; t.k = c->p.k;
+    return t;
+}
+
+static int alloc_hash(pg_ctx* ctx, uint64_t slots)
+{
+    CK(cudaSetDevice(ctx->p.device));
+    ctx->n_slots = slots;
+    CK(cudaMalloc((void**)&ctx->keys, slots * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&ctx->counts, slots * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->keys, 0xFF, slots * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->counts, 0, slots * sizeof(uint32_t), ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_create(const pg_params* p, pg_ctx** out)
+{
+    pg_ctx* ctx = nullptr;
+    if (!p || !out) return fail(nullptr, PG_ERR_INVALID, "pg_create: null argument");
+    *out = nullptr;
+    if (p->k < 1 || p->k > 31) return fail(nullptr, PG_ERR_INVALID, "k must be in 1..31");
+    if (p->tnf_k < 1 || p->tnf_k > 6) return fail(nullptr, PG_ERR_INVALID, "tnf_k must be in 1..6");
+    if (p->window_size < 1) return fail(nullptr, PG_ERR_INVALID, "window_size must be >= 1");
+    if (p->vector_size < 1 || p->vector_size > 8192) return fail(nullptr, PG_ERR_INVALID, "vector_size must be in 1..8192");
+    int mode = p->table_mode == PG_TABLE_AUTO ? (p->k <= 16 ? PG_TABLE_DENSE : PG_TABLE_HASH) : p->table_mode;
+    if (mode == PG_TABLE_DENSE && p->k > 16) return fail(nullptr, PG_ERR_INVALID, "dense table needs k <= 16");
+    if (mode != PG_TABLE_DENSE && mode != PG_TABLE_HASH) return fail(nullptr, PG_ERR_INVALID, "bad table_mode");
+    if (p->table_capacity & (p->table_capacity - 1)) return fail(nullptr, PG_ERR_INVALID, "table_capacity must be a power of two");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(nullptr, PG_ERR_CUDA, "no CUDA device: pangaea_b200 has no CPU path");
+    if (p->device < 0 || p->device >= n_dev) return fail(nullptr, PG_ERR_INVALID, "bad device ordinal");
+
+    ctx = new (std::nothrow) pg_ctx();
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "out of host memory");
+    ctx->p = *p;
+    ctx->mode = mode == PG_TABLE_DENSE ? kDense : kHash;
+    std::vector<uint16_t> lut;
+    ctx->td = build_tnf_lut(p->tnf_k, &lut);
+#define CKC(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            int rc_ = fail(nullptr, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+            pg_destroy(ctx);                                                                             \
+            return rc_;                                                                                  \
+        }                                                                                                \
+    } while (0)
+    CKC(cudaSetDevice(p->device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    {   // keep freed blocks in the pool: steady-state steps allocate without touching the driver
+        cudaMemPool_t pool;
+        CKC(cudaDeviceGetDefaultMemPool(&pool, p->device));
+        uint64_t keep = ~0ull;
+        CKC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    CKC(cudaMalloc((void**)&ctx->d_lut, lut.size() * sizeof(uint16_t)));
+    CKC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CKC(cudaMalloc((void**)&ctx->d_overflow, sizeof(uint32_t)));
+    CKC(cudaMemset(ctx->d_overflow, 0, sizeof(uint32_t)));
+    CKC(cudaMalloc((void**)&ctx->d_scalar, 8 * sizeof(int64_t)));
+    CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
+    if (ctx->mode == kDense) {
+        ctx->n_slots = dense_entries(p->k);
+        CKC(cudaMalloc((void**)&ctx->counts, ctx->n_slots * sizeof(uint32_t)));
+        CKC(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
+    } else if (p->table_capacity) {
+        int rc = alloc_hash(ctx, p->table_capacity);
+        if (rc != PG_OK) { pg_destroy(ctx); return rc; }
+    }
+    CKC(cudaFuncSetAttribute(featurize_kernel<kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaFuncSetAttribute(featurize_kernel<kHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+    *out = ctx;
+    return PG_OK;
+}
+
+extern "C" void pg_destroy(pg_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->p.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : ctx->pool) cudaEventDestroy(e);
+    cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int pg_synchronize(pg_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(ctx->p.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" void* pg_stream(pg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------
+extern "C" int pg_timing_reset(pg_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& s : ctx->spans) { ctx->pool.push_back(s.a); ctx->pool.push_back(s.b); }
+    ctx->spans.clear();
+    memset(ctx->launches, 0, sizeof(ctx->launches));
+    return PG_OK;
+}
+
+extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* launches_out)
+{
+    if (!ctx || which < 0 || which > T_ALL) return fail(ctx, PG_ERR_INVALID, "pg_timing_get: bad argument");
+    CK(cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    int64_t n = 0;
+    for (auto& s : ctx->spans)
+        if (which == T_ALL || s.which == which) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, s.a, s.b));
+            ms += t;
+        }
+    for (int i = 0; i < 5; ++i)
+        if (which == T_ALL || i == which) n += ctx->launches[i];
+    if (ms_out) *ms_out = ms;
+    if (launches_out) *launches_out = n;
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------
+static int pack_batch(pg_ctx* ctx, pg_batch* b)
+{
+    b->n_words = (b->n_bytes + 31) / 32;
+    CK(dmalloc(ctx, &b->codes, (size_t)b->n_words + 2));
+    CK(dmalloc(ctx, &b->maskF, (size_t)b->n_words + 2));
+    CK(dmalloc(ctx, &b->maskC, (size_t)b->n_words + 2));
+    {
+        Timed t(ctx, T_PACK, 1);
+        pack_kernel<<<grid_for(b->n_words + 2, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            b->seq, b->qual, b->n_bytes, b->n_words, (uint32_t)ctx->p.min_qual_char, b->codes, b->maskF, b->maskC);
+    }
+    CK(cudaGetLastError());
+    return PG_OK;
+}
+
+static int check_reads(pg_ctx* ctx, const pg_reads* r)
+{
+    if (!ctx || !r) return fail(ctx, PG_ERR_INVALID, "null argument");
+    if (r->n_reads < 0 || r->n_bytes < 0) return fail(ctx, PG_ERR_INVALID, "negative batch size");
+    if (r->n_reads > 0 && (!r->seq || !r->read_off || !r->read_flag)) return fail(ctx, PG_ERR_INVALID, "null batch arrays");
+    if (ctx->p.min_qual_char && !r->qual && r->n_bytes) return fail(ctx, PG_ERR_INVALID, "min_qual_char set but the batch carries no qualities");
+    return PG_OK;
+}
+
+extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
+{
+    int rc = check_reads(ctx, h);
+    if (rc) return rc;
+    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (h->n_reads > 0 && (h->read_off[0] != 0 || h->read_off[h->n_reads] != h->n_bytes))
+        return fail(ctx, PG_ERR_INVALID, "read_off must start at 0 and end at n_bytes");
+    CK(cudaSetDevice(ctx->p.device));
+    pg_batch* b = new pg_batch();
+    b->owns = true;
+    b->n_reads = h->n_reads;
+    b->n_bytes = h->n_bytes;
+    const size_t padded = ((size_t)h->n_bytes + 63) & ~(size_t)31;
+    bool ok = dmalloc(ctx, &b->seq, padded) == cudaSuccess && dmalloc(ctx, &b->read_off, (size_t)h->n_reads + 1) == cudaSuccess &&
+              dmalloc(ctx, &b->read_flag, (size_t)h->n_reads) == cudaSuccess;
+    const bool want_q = ctx->p.min_qual_char && h->qual;
+    if (ok && want_q) ok = dmalloc(ctx, &b->qual, padded) == cudaSuccess;
+    if (!ok) { pg_batch_free(ctx, b); return fail(ctx, PG_ERR_CUDA, "pg_batch_upload: device allocation failed"); }
+    if (h->n_reads) {
+        cudaMemcpyAsync(b->seq, h->seq, (size_t)h->n_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (want_q) cudaMemcpyAsync(b->qual, h->qual, (size_t)h->n_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(b->read_off, h->read_off, ((size_t)h->n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(b->read_flag, h->read_flag, (size_t)h->n_reads, cudaMemcpyHostToDevice, ctx->stream);
+    } else {
+        cudaMemsetAsync(b->read_off, 0, sizeof(int64_t), ctx->stream);
+    }
+    rc = pack_batch(ctx, b);
+    if (rc == PG_OK && cudaGetLastError() != cudaSuccess) rc = fail(ctx, PG_ERR_CUDA, "pg_batch_upload: copy failed");
+    if (rc) { pg_batch_free(ctx, b); return rc; }
+    *out = b;
+    return PG_OK;
+}
+
+extern "C" int pg_batch_adopt(pg_ctx* ctx, const pg_reads* d, pg_batch** out)
+{
+    int rc = check_reads(ctx, d);
+    if (rc) return rc;
+    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (((uintptr_t)d->seq & 15) || (d->qual && ((uintptr_t)d->qual & 15))) return fail(ctx, PG_ERR_INVALID, "seq/qual must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->p.device));
+    pg_batch* b = new pg_batch();
+    b->owns = false;
+    b->seq = const_cast<uint8_t*>(d->seq);
+    b->qual = ctx->p.min_qual_char ? const_cast<uint8_t*>(d->qual) : nullptr;
+    b->read_off = const_cast<int64_t*>(d->read_off);
+    b->read_flag = const_cast<uint8_t*>(d->read_flag);
+    b->n_reads = d->n_reads;
+    b->n_bytes = d->n_bytes;
+    rc = pack_batch(ctx, b);
+    if (rc) { pg_batch_free(ctx, b); return rc; }
+    *out = b;
+    return PG_OK;
+}
+
+extern "C" void pg_batch_free(pg_ctx* ctx, pg_batch* b)
+{
+    if (!b || !ctx) return;
+    cudaSetDevice(ctx->p.device);
+    if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); dfree(ctx, b->read_off); dfree(ctx, b->read_flag); }
+    dfree(ctx, b->codes); dfree(ctx, b->maskF); dfree(ctx, b->maskC);
+    delete b;
+}
+
+// ---------------------------------------------------------------------------
+// table
+// ---------------------------------------------------------------------------
+extern "C" int pg_table_clear(pg_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(ctx->p.device));
+    if (ctx->counts) CK(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
+    if (ctx->keys) CK(cudaMemsetAsync(ctx->keys, 0xFF, ctx->n_slots * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(uint32_t), ctx->stream));
+    ctx->counted = false;
+    return PG_OK;
+}
+
+static int ensure_table(pg_ctx* ctx, int64_t hint_windows)
+{
+    if (ctx->counts) return PG_OK;
+    // hash mode, capacity not given: 2x the number of windows of the first batch, within [2^20, 2^33]
+    uint64_t want = 2 * (uint64_t)std::max<int64_t>(hint_windows, 1), slots = 1ull << 20;
+    while (slots < want && slots < (1ull << 33)) slots <<= 1;
+    return alloc_hash(ctx, slots);
+}
+
+static int check_overflow(pg_ctx* ctx)
+{
+    if (ctx->mode != kHash) return PG_OK;
+    uint32_t of = 0;
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(&of, ctx->h_pin, sizeof(of));
+    if (of) return fail(ctx, PG_ERR_CAPACITY, "k-mer hash table is full: raise pg_params.table_capacity");
+    return PG_OK;
+}
+
+extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
+{
+    if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->p.device));
+    int rc = ensure_table(ctx, b->n_bytes);
+    if (rc) return rc;
+    if (b->n_words) {
+        Timed t(ctx, T_COUNT, 1);
+        const int grid = grid_for(b->n_words, 256, ctx->sm_count * 8);
+        if (ctx->mode == kDense) count_kernel<kDense><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, b->n_words, view(ctx));
+        else count_kernel<kHash><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, b->n_words, view(ctx));
+    }
+    CK(cudaGetLastError());
+    ctx->counted = true;
+    return check_overflow(ctx);
+}
+
+extern "C" int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* counts, int64_t n)
+{
+    if (!ctx || (n > 0 && (!keys || !counts)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_set: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    int rc = ensure_table(ctx, n);
+    if (rc) return rc;
+    ctx->counted = true;
+    if (!n) return PG_OK;
+    uint64_t* dk; uint32_t* dc;
+    CK(dmalloc(ctx, &dk, (size_t)n)); CK(dmalloc(ctx, &dc, (size_t)n));
+    // one key at a time keeps "last assignment wins" (count_kmer.cpp:166) for duplicate keys:
+    // duplicates are resolved on the host, in order, before the scatter
+    std::vector<uint64_t> hk(keys, keys + n);
+    std::vector<uint32_t> hc(counts, counts + n);
+    {
+        std::vector<int64_t> order(n);
+        for (int64_t i = 0; i < n; ++i) order[i] = i;
+        auto canon = [&](int64_t i) { return canonical_of_fwd(hk[i] & low_mask64(2 * ctx->p.k), ctx->p.k); };
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b2) { return canon(a) < canon(b2); });
+        std::vector<uint64_t> k2; std::vector<uint32_t> c2;
+        for (int64_t i = 0; i < n; ++i) {
+            const bool last = (i + 1 == n) || canon(order[i + 1]) != canon(order[i]);
+            if (last) { k2.push_back(hk[order[i]]); c2.push_back(hc[order[i]]); }
+        }
+        hk.swap(k2); hc.swap(c2);
+    }
+    const int64_t m = (int64_t)hk.size();
+    CK(cudaMemcpyAsync(dk, hk.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dc, hc.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    table_set_kernel<<<(int)((m + 255) / 256), 256, 0, ctx->stream>>>(view(ctx), ctx->mode, dk, dc, m);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream)); // hk/hc are about to go out of scope
+    dfree(ctx, dk); dfree(ctx, dc);
+    return check_overflow(ctx);
+}
+
+extern "C" int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* out, int64_t n)
+{
+    if (!ctx || (n > 0 && (!keys || !out)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_get: bad argument");
+    if (!n) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    if (!ctx->counts) { memset(out, 0, (size_t)n * sizeof(uint32_t)); return PG_OK; }
+    uint64_t* dk; uint32_t* dc;
+    CK(dmalloc(ctx, &dk, (size_t)n)); CK(dmalloc(ctx, &dc, (size_t)n));
+    CK(cudaMemcpyAsync(dk, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    table_get_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(view(ctx), ctx->mode, dk, dc, n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, dk); dfree(ctx, dc);
+    return PG_OK;
+}
+
+extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
+{
+    if (!ctx || !n_distinct) return fail(ctx, PG_ERR_INVALID, "pg_table_size: bad argument");
+    *n_distinct = 0;
+    if (!ctx->counts) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
+    table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, (unsigned long long*)ctx->d_scalar);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_distinct = ctx->h_pin[0];
+    return PG_OK;
+}
+
+extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts_out, int64_t cap, int64_t* n_out)
+{
+    if (!ctx || !keys_out || !counts_out || cap < 0 || !n_out) return fail(ctx, PG_ERR_INVALID, "pg_table_export: bad argument");
+    *n_out = 0;
+    if (!ctx->counts || !cap) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    uint64_t* dk; uint32_t* dc;
+    CK(dmalloc(ctx, &dk, (size_t)cap)); CK(dmalloc(ctx, &dc, (size_t)cap));
+    CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
+    table_export_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(view(ctx), ctx->mode, ctx->n_slots, dk, dc, (unsigned long long)cap,
+                                                                    (unsigned long long*)ctx->d_scalar);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t n = std::min<int64_t>(ctx->h_pin[0], cap);
+    std::vector<uint64_t> hk(n); std::vector<uint32_t> hc(n);
+    CK(cudaMemcpyAsync(hk.data(), dk, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hc.data(), dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, dk); dfree(ctx, dc);
+    std::vector<int64_t> order(n);
+    for (int64_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return hk[a] < hk[b]; });
+    for (int64_t i = 0; i < n; ++i) { keys_out[i] = hk[order[i]]; counts_out[i] = hc[order[i]]; }
+    *n_out = n;
+    if (ctx->h_pin[0] > cap) return fail(ctx, PG_ERR_INVALID, "pg_table_export: buffer too small");
+    return PG_OK;
+}
+
+extern "C" int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entries)
+{
+    if (!ctx || !dev_ptr || !n_entries) return fail(ctx, PG_ERR_INVALID, "pg_table_dense_view: bad argument");
+    if (ctx->mode != kDense) return fail(ctx, PG_ERR_STATE, "pg_table_dense_view: table is not dense");
+    *dev_ptr = ctx->counts;
+    *n_entries = (int64_t)ctx->n_slots;
+    ctx->counted = true; // a caller that sums tables across ranks owns the contents
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// grouping + featurize
+// ---------------------------------------------------------------------------
+// exclusive scan of (flags & bit) in tiles; returns device tile offsets (caller frees) and the total
+static int scan_flags(pg_ctx* ctx, const uint8_t* d_flags, int64_t n, uint32_t bit, int32_t** tile_off_out, int64_t* total_out)
+{
+    const int64_t n_tiles = std::max<int64_t>(1, (n + kScanTile - 1) / kScanTile);
+    int32_t* tile_off;
+    CK(dmalloc(ctx, &tile_off, (size_t)n_tiles));
+    flag_count_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(d_flags, n, bit, tile_off);
+    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(tile_off, n_tiles, ctx->d_scalar);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total_out = ctx->h_pin[0];
+    *tile_off_out = tile_off;
+    return PG_OK;
+}
+
+extern "C" int64_t pg_batch_n_groups(const pg_batch* b) { return b ? b->n_groups : -1; }
+
+extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
+{
+    if (!ctx || !b || !out || n_groups < 1 || !group_keep) return fail(ctx, PG_ERR_INVALID, "pg_featurize: bad argument");
+    *out = nullptr;
+    if (!ctx->counted || !ctx->counts) return fail(ctx, PG_ERR_STATE, "pg_featurize: the k-mer table is empty - call pg_count / pg_table_set first");
+    if (n_groups > 0x7FFFFFFFll) return fail(ctx, PG_ERR_INVALID, "more than 2^31 clouds in one batch");
+    CK(cudaSetDevice(ctx->p.device));
+
+    int64_t* gstart = nullptr;
+    unsigned long long* nofeat_len = nullptr;
+    uint8_t *d_keep = nullptr, *emit = nullptr;
+    int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr;
+    int64_t changes = 0, nofeat = 0, rows = 0;
+    int rc = PG_OK;
+    pg_features* f = nullptr;
+    auto cleanup = [&]() {
+        dfree(ctx, gstart); dfree(ctx, nofeat_len); dfree(ctx, d_keep); dfree(ctx, emit);
+        dfree(ctx, row_of_group); dfree(ctx, group_of_row_full);
+    };
+#define CKF(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                   \
+            if (f) pg_features_free(ctx, f);                                                             \
+            return fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+        }                                                                                                \
+    } while (0)
+
+    // ---- grouping --------------------------------------------------------
+    {
+        Timed t(ctx, T_GROUP, 8);
+        CKF(dmalloc(ctx, &gstart, (size_t)n_groups + 1));
+        CKF(dmalloc(ctx, &nofeat_len, (size_t)n_groups));
+        CKF(dmalloc(ctx, &d_keep, (size_t)n_groups));
+        CKF(dmalloc(ctx, &emit, (size_t)n_groups));
+        CKF(dmalloc(ctx, &row_of_group, (size_t)n_groups));
+        CKF(dmalloc(ctx, &group_of_row_full, (size_t)n_groups));
+        CKF(cudaMemsetAsync(nofeat_len, 0, (size_t)n_groups * sizeof(unsigned long long), ctx->stream));
+        CKF(cudaMemcpyAsync(d_keep, group_keep, (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
+
+        // PG_READ_NOFEAT reads are rare; when present their bases are masked out of maskF
+        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_NOFEAT, &tile_off, &nofeat);
+        if (rc) { cleanup(); return rc; }
+        dfree(ctx, tile_off);
+        if (nofeat)
+            clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, b->maskF);
+
+        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_CHANGE, &tile_off, &changes);
+        if (rc) { cleanup(); return rc; }
+        b->n_groups = changes + 1;
+        if (b->n_groups != n_groups) {
+            dfree(ctx, tile_off); cleanup();
+            return fail(ctx, PG_ERR_INVALID, "pg_featurize: n_groups (" + std::to_string(n_groups) + ") != 1 + change flags (" + std::to_string(changes + 1) + ")");
+        }
+        {
+            const int64_t n_tiles = std::max<int64_t>(1, (b->n_reads + kScanTile - 1) / kScanTile);
+            if (b->n_reads == 0) {
+                CKF(cudaMemsetAsync(gstart, 0, 2 * sizeof(int64_t), ctx->stream));
+            } else {
+                group_starts_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(b->read_flag, b->read_off, b->n_reads, tile_off, n_groups, gstart, nofeat_len);
+            }
+        }
+        dfree(ctx, tile_off);
+        group_emit_kernel<<<(int)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(gstart, nofeat_len, d_keep, n_groups, ctx->p.min_length, emit);
+        CKF(cudaGetLastError());
+        rc = scan_flags(ctx, emit, n_groups, 1u, &tile_off, &rows);
+        if (rc) { cleanup(); return rc; }
+        {
+            const int64_t n_tiles = std::max<int64_t>(1, (n_groups + kScanTile - 1) / kScanTile);
+            row_assign_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(emit, n_groups, tile_off, row_of_group, group_of_row_full);
+        }
+        dfree(ctx, tile_off);
+        CKF(cudaGetLastError());
+    }
+
+    // ---- output matrices ---------------------------------------------------
+    f = new pg_features();
+    f->device = ctx->p.device;
+    f->rows = rows;
+    f->vs = ctx->p.vector_size;
+    f->td = ctx->td;
+    CKF(dmalloc(ctx, &f->abd_raw, (size_t)rows * f->vs));
+    CKF(dmalloc(ctx, &f->tnf_raw, (size_t)rows * f->td));
+    CKF(dmalloc(ctx, &f->group_of_row, (size_t)rows));
+    CKF(cudaMemsetAsync(f->abd_raw, 0, (size_t)rows * f->vs * sizeof(uint32_t), ctx->stream));
+    CKF(cudaMemsetAsync(f->tnf_raw, 0, (size_t)rows * f->td * sizeof(uint32_t), ctx->stream));
+    if (rows) CKF(cudaMemcpyAsync(f->group_of_row, group_of_row_full, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+
+    // ---- the pass over the bases -------------------------------------------
+    if (rows && b->n_words) {
+        FeatParams P;
+        P.codes = b->codes; P.maskF = b->maskF; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
+        P.gstart = gstart; P.n_groups = n_groups; P.row_of_group = row_of_group;
+        P.tnf_k = ctx->p.tnf_k; P.vs = f->vs; P.td = f->td;
+        P.ws = (uint32_t)ctx->p.window_size;
+        const uint64_t clamp64 = (uint64_t)P.ws * (uint64_t)P.vs;
+        P.clamp = clamp64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)clamp64;
+        // q = (c * ceil(2^32 / ws)) >> 32 equals c / ws for every c < 2^32 / ws; c < clamp = ws * vs
+        P.use_magic = (P.ws > 1 && (uint64_t)P.ws * clamp64 < (1ull << 32)) ? 1 : 0;
+        P.magic = P.use_magic ? (uint32_t)(((1ull << 32) + P.ws - 1) / P.ws) : 0u;
+        P.lut = ctx->d_lut;
+        P.abd = f->abd_raw; P.tnf = f->tnf_raw;
+        P.table = view(ctx);
+        const size_t smem = (size_t)kSlots * (P.vs + P.td) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
+        int occ = 1;
+        if (ctx->mode == kDense) CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, featurize_kernel<kDense>, kFeatThreads, smem));
+        else CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, featurize_kernel<kHash>, kFeatThreads, smem));
+        if (occ < 1) { cleanup(); pg_features_free(ctx, f); return fail(ctx, PG_ERR_INVALID, "vector_size / tnf_k too large for shared memory"); }
+        const int64_t n_cta = std::min<int64_t>((int64_t)ctx->sm_count * occ, (b->n_words + kFeatThreads - 1) / kFeatThreads);
+        int64_t wpc = (b->n_words + n_cta - 1) / n_cta;
+        wpc = (wpc + kFeatThreads - 1) / kFeatThreads * kFeatThreads;
+        P.words_per_cta = wpc;
+        const int grid = (int)((b->n_words + wpc - 1) / wpc);
+        Timed t(ctx, T_FEAT, 1);
+        if (ctx->mode == kDense) featurize_kernel<kDense><<<grid, kFeatThreads, smem, ctx->stream>>>(P);
+        else featurize_kernel<kHash><<<grid, kFeatThreads, smem, ctx->stream>>>(P);
+    }
+    CKF(cudaGetLastError());
+    cleanup();
+#undef CKF
+    *out = f;
+    return PG_OK;
+}
+
+static void features_release(pg_features* f)
+{
+    if (--f->refs > 0) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->abd_raw); cudaFree(f->tnf_raw); cudaFree(f->abd); cudaFree(f->tnf); cudaFree(f->weights); cudaFree(f->group_of_row);
+    delete f;
+}
+
+extern "C" void pg_features_free(pg_ctx* ctx, pg_features* f)
+{
+    (void)ctx;
+    if (f) features_release(f);
+}
+
+extern "C" int64_t pg_features_rows(const pg_features* f) { return f ? f->rows : -1; }
+extern "C" int32_t pg_features_abd_dim(const pg_features* f) { return f ? f->vs : -1; }
+extern "C" int32_t pg_features_tnf_dim(const pg_features* f) { return f ? f->td : -1; }
+
+extern "C" int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t* groups_out)
+{
+    if (!ctx || !f || (f->rows && !groups_out)) return fail(ctx, PG_ERR_INVALID, "pg_features_row_groups: bad argument");
+    if (!f->rows) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    std::vector<int32_t> tmp(f->rows);
+    CK(cudaMemcpyAsync(tmp.data(), f->group_of_row, (size_t)f->rows * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < f->rows; ++i) groups_out[i] = tmp[i];
+    return PG_OK;
+}
+
+extern "C" int pg_features_copy_raw(pg_ctx* ctx, const pg_features* f, int32_t* abd_out, int32_t* tnf_out)
+{
+    if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_features_copy_raw: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    if (abd_out && f->rows) CK(cudaMemcpyAsync(abd_out, f->abd_raw, (size_t)f->rows * f->vs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tnf_out && f->rows) CK(cudaMemcpyAsync(tnf_out, f->tnf_raw, (size_t)f->rows * f->td * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Data.__init__
+// ---------------------------------------------------------------------------
+extern "C" int pg_normalize(pg_ctx* ctx, pg_features* f)
+{
+    if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_normalize: bad argument");
+    if (f->normalized) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    CK(dmalloc(ctx, &f->abd, (size_t)f->rows * f->vs));
+    CK(dmalloc(ctx, &f->tnf, (size_t)f->rows * f->td));
+    CK(dmalloc(ctx, &f->weights, (size_t)f->rows));
+    if (f->rows) {
+        Timed t(ctx, T_NORM, 2);
+        const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
+        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights);
+        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr);
+    }
+    CK(cudaGetLastError());
+    f->normalized = true;
+    return PG_OK;
+}
+
+extern "C" int pg_features_from_raw(pg_ctx* ctx, const uint32_t* abd, const uint32_t* tnf, int64_t rows, int32_t abd_dim, int32_t tnf_dim, pg_features** out)
+{
+    if (!ctx || !out || rows < 0 || abd_dim < 1 || tnf_dim < 1 || (rows && (!abd || !tnf))) return fail(ctx, PG_ERR_INVALID, "pg_features_from_raw: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->p.device));
+    pg_features* f = new pg_features();
+    f->device = ctx->p.device; f->rows = rows; f->vs = abd_dim; f->td = tnf_dim;
+    cudaError_t e = dmalloc(ctx, &f->abd_raw, (size_t)rows * abd_dim);
+    if (e == cudaSuccess) e = dmalloc(ctx, &f->tnf_raw, (size_t)rows * tnf_dim);
+    if (e == cudaSuccess) e = dmalloc(ctx, &f->group_of_row, (size_t)rows);
+    if (e == cudaSuccess && rows) e = cudaMemcpyAsync(f->abd_raw, abd, (size_t)rows * abd_dim * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && rows) e = cudaMemcpyAsync(f->tnf_raw, tnf, (size_t)rows * tnf_dim * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && rows) e = cudaMemsetAsync(f->group_of_row, 0, (size_t)rows * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { pg_features_free(ctx, f); return fail(ctx, PG_ERR_CUDA, std::string("pg_features_from_raw: ") + cudaGetErrorString(e)); }
+    *out = f;
+    return PG_OK;
+}
+
+extern "C" int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, float* abd_out, float* tnf_out, double* weights_out)
+{
+    if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_features_copy_normalized: bad argument");
+    if (!f->normalized) return fail(ctx, PG_ERR_STATE, "call pg_normalize first");
+    CK(cudaSetDevice(ctx->p.device));
+    if (abd_out && f->rows) CK(cudaMemcpyAsync(abd_out, f->abd, (size_t)f->rows * f->vs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tnf_out && f->rows) CK(cudaMemcpyAsync(tnf_out, f->tnf, (size_t)f->rows * f->td * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weights_out && f->rows) CK(cudaMemcpyAsync(weights_out, f->weights, (size_t)f->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" void* pg_features_device_ptr(const pg_features* f, int which)
+{
+    if (!f) return nullptr;
+    switch (which) {
+    case 0: return f->abd_raw;
+    case 1: return f->tnf_raw;
+    case 2: return f->abd;
+    case 3: return f->tnf;
+    case 4: return f->weights;
+    default: return nullptr;
+    }
+}
+
+// ---- DLPack (v0.8 ABI, declared locally: no external header needed) -----------
+namespace {
+struct DLDevice { int32_t device_type; int32_t device_id; };
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor { void* data; DLDevice device; int32_t ndim; DLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DLManagedTensor { DLTensor dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor*); };
+struct DlHolder { DLManagedTensor mt; int64_t shape[2]; pg_features* f; };
+void dl_deleter(DLManagedTensor* mt)
+{
+    DlHolder* h = reinterpret_cast<DlHolder*>(mt->manager_ctx);
+    features_release(h->f);
+    delete h;
+}
+} // namespace
+
+extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
+{
+    if (!ctx || !f || which < 0 || which > 4) { fail(ctx, PG_ERR_INVALID, "pg_features_dlpack: bad argument"); return nullptr; }
+    if (which >= 2 && !f->normalized) { fail(ctx, PG_ERR_STATE, "call pg_normalize first"); return nullptr; }
+    cudaSetDevice(ctx->p.device);
+    cudaStreamSynchronize(ctx->stream); // the consumer runs on its own stream
+    DlHolder* h = new DlHolder();
+    h->f = f;
+    ++f->refs;
+    DLTensor& t = h->mt.dl_tensor;
+    t.data = pg_features_device_ptr(f, which);
+    t.device = { 2 /* kDLCUDA */, f->device };
+    t.byte_offset = 0;
+    t.strides = nullptr;
+    t.shape = h->shape;
+    h->shape[0] = f->rows;
+    if (which == 4) { t.ndim = 1; t.dtype = { 2 /* float */, 64, 1 }; }
+    else {
+        t.ndim = 2;
+        h->shape[1] = (which == 0 || which == 2) ? f->vs : f->td;
+        t.dtype = which < 2 ? DLDataType{ 0 /* int */, 32, 1 } : DLDataType{ 2, 32, 1 };
+    }
+    h->mt.manager_ctx = h;
+    h->mt.deleter = dl_deleter;
+    return &h->mt;
+}
+
+// ---------------------------------------------------------------------------
+// whole path, host buffers in
+// ---------------------------------------------------------------------------
+extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
+{
+    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
+    *out = nullptr;
+    int rc = pg_table_clear(ctx);
+    if (rc) return rc;
+    pg_batch* b = nullptr;
+    rc = pg_batch_upload(ctx, host, &b);
+    if (rc) return rc;
+    rc = pg_count(ctx, b);
+    pg_features* f = nullptr;
+    if (!rc) rc = pg_featurize(ctx, b, group_keep, n_groups, &f);
+    if (!rc) rc = pg_normalize(ctx, f);
+    pg_batch_free(ctx, b);
+    if (rc) { if (f) pg_features_free(ctx, f); return rc; }
+    *out = f;
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic reads (bench input)
+// ---------------------------------------------------------------------------
+extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
+                                 const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
+                                 double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag)
+{
+    if (!ctx || n_pairs < 0 || read_len < 1 || n_barcodes < 1 || !d_bc_start || !d_bc_genome || !d_seq || !d_read_off || !d_read_flag)
+        return fail(ctx, PG_ERR_INVALID, "pg_synth_generate: bad argument");
+    if (insert < read_len || frag_len < insert || genome_len < frag_len) return fail(ctx, PG_ERR_INVALID, "need read_len <= insert <= frag_len <= genome_len");
+    CK(cudaSetDevice(ctx->p.device));
+    SynthParams S;
+    S.n_pairs = n_pairs; S.read_len = read_len; S.n_barcodes = n_barcodes; S.bc_start = d_bc_start; S.bc_genome = d_bc_genome;
+    S.genome_len = genome_len; S.frag_len = frag_len; S.insert = insert;
+    S.sub_thresh = (uint32_t)std::min(4294967295.0, sub_rate * 4294967296.0);
+    S.n_thresh = (uint32_t)std::min(4294967295.0, n_rate * 4294967296.0);
+    S.seed = seed;
+    synth_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(S, d_seq, d_read_off, d_read_flag);
+    synth_flags_kernel<<<(int)((n_barcodes + 255) / 256), 256, 0, ctx->stream>>>(S, d_read_flag);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}

@@ -1,0 +1,120 @@
+// table.cuh - the global canonical k-mer count table resident in HBM.
+//
+// Stands for jellyfish's hash + `dump` + the unordered_map that count_kmer rebuilds
+// from the dump text (src/feature.py:76-103, src/cpptools/count_kmer.cpp:139-170).
+// Two layouts behind one view:
+//   DENSE (k <= 16): direct-addressed u32 counters, index = dense_index (kmer.cuh);
+//         the degenerate open-addressing table whose hash is the identity and whose
+//         probe sequence has length 1.  k = 15 (the production default): 2^29
+//         counters = 2 GiB - 1 % of a B200's HBM.
+//   HASH  (k <= 31): lock-free open addressing, linear probing, u64 keys claimed with
+//         atomicCAS, u32 counters bumped with atomicAdd (no-return => RED).
+// Counter updates are fire-and-forget reductions; nothing waits on a round trip.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "kmer.cuh"
+
+namespace pg {
+
+constexpr uint64_t kEmptyKey = ~0ull;
+enum TableMode { kDense = 0, kHash = 1 };
+
+struct TableView {
+    uint32_t* counts;              // dense: counters; hash: values
+    unsigned long long* keys;      // hash only
+    uint64_t capacity_mask;        // hash: slots - 1
+    uint32_t* overflow;            // hash: set to 1 when an insert finds no slot
+    int k;
+};
+
+__device__ __forceinline__ void table_add_dense(const TableView& t, uint32_t idx, uint32_t n)
+{
+    atomicAdd(t.counts + idx, n); // result unused -> RED.E.ADD
+}
+
+__device__ __forceinline__ void table_add_hash(const TableView& t, uint64_t key, uint32_t n)
+{
+    uint64_t slot = mix64(key) & t.capacity_mask;
+    for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
+        unsigned long long cur = *((volatile unsigned long long*)(t.keys + slot));
+        if (cur == kEmptyKey) cur = atomicCAS(t.keys + slot, kEmptyKey, (unsigned long long)key);
+        if (cur == kEmptyKey || cur == key) {
+            atomicAdd(t.counts + slot, n);
+            return;
+        }
+        slot = (slot + 1) & t.capacity_mask;
+    }
+    *t.overflow = 1u;
+}
+
+__device__ __forceinline__ uint32_t table_get_hash(const TableView& t, uint64_t key)
+{
+    uint64_t slot = mix64(key) & t.capacity_mask;
+    for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
+        unsigned long long cur = __ldg(t.keys + slot);
+        if (cur == key) return __ldg(t.counts + slot);
+        if (cur == kEmptyKey) return 0u;
+        slot = (slot + 1) & t.capacity_mask;
+    }
+    return 0u;
+}
+
+// --- host-driven table maintenance (parity tooling; off the hot path) ---------
+
+// kmer2frequency[key] = count  (count_kmer.cpp:166) - keys arrive as forward values
+__global__ void table_set_kernel(TableView t, int mode, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = keys[i] & low_mask64(2 * t.k);
+    if (mode == kDense) {
+        t.counts[dense_index_of_fwd(v, t.k)] = counts[i];
+    } else {
+        uint64_t key = canonical_of_fwd(v, t.k);
+        uint64_t slot = mix64(key) & t.capacity_mask;
+        for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
+            unsigned long long cur = atomicCAS(t.keys + slot, kEmptyKey, (unsigned long long)key);
+            if (cur == kEmptyKey || cur == key) { t.counts[slot] = counts[i]; return; }
+            slot = (slot + 1) & t.capacity_mask;
+        }
+        *t.overflow = 1u;
+    }
+}
+
+__global__ void table_get_kernel(TableView t, int mode, const uint64_t* __restrict__ keys, uint32_t* __restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = keys[i] & low_mask64(2 * t.k);
+    out[i] = mode == kDense ? t.counts[dense_index_of_fwd(v, t.k)] : table_get_hash(t, canonical_of_fwd(v, t.k));
+}
+
+// number of non-zero counters (distinct k-mers)
+__global__ void table_nonzero_kernel(const uint32_t* __restrict__ counts, uint64_t n, unsigned long long* __restrict__ total)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += counts[i] != 0;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+
+// unordered export of (reference canonical key, count) for non-zero counters
+__global__ void table_export_kernel(TableView t, int mode, uint64_t n_slots, uint64_t* __restrict__ keys_out,
+                                    uint32_t* __restrict__ counts_out, unsigned long long cap, unsigned long long* __restrict__ cursor)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint32_t c = t.counts[i];
+        if (!c) continue;
+        unsigned long long at = atomicAdd(cursor, 1ull);
+        if (at < cap) {
+            keys_out[at] = mode == kDense ? key_of_dense_index(i, t.k) : (uint64_t)t.keys[i];
+            counts_out[at] = c;
+        }
+    }
+}
+
+} // namespace pg

@@ -1,0 +1,101 @@
+"""CPU: the product's host FASTQ reader (csrc/fastq.cpp) + the batch contract of
+include/pangaea_b200.h, checked against the golden outputs of the reference binaries and
+against the oracle.  No GPU compute is called."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import contract_features
+from pangaea_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/pangaea_b200.h is exported and bound."""
+    hdr = open(os.path.join(ROOT, "include", "pangaea_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_device_fails_loudly():
+    L = _lib.lib()
+    if L.pg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.PgError, match="no CPU path"):
+        _lib.Context()
+
+
+def test_param_validation_without_device():
+    L = _lib.lib()
+    p = _lib.pg_params()
+    L.pg_default_params(C.byref(p))
+    assert (p.k, p.tnf_k, p.window_size, p.vector_size, p.min_length) == (15, 4, 10, 400, 2000)
+    h = C.c_void_p()
+    for field, bad in (("k", 0), ("k", 32), ("tnf_k", 7), ("window_size", 0), ("vector_size", 0), ("table_capacity", 3)):
+        q = _lib.pg_params()
+        L.pg_default_params(C.byref(q))
+        setattr(q, field, bad)
+        assert L.pg_create(C.byref(q), C.byref(h)) == -1, field
+    assert [L.pg_tnf_dim(k) for k in (1, 2, 3, 4, 5, 6)] == [2, 10, 32, 136, 512, 2080]
+
+
+def test_parser_contract_reproduces_reference_outputs(golden, oracle):
+    p = golden.params
+    fq = _lib.Fastq(golden.path1, golden.reads2)
+    seq, off, flag, keep = fq.arrays()
+    labels = [fq.label(g) for g in range(fq.n_groups)]
+    assert off[0] == 0 and off[-1] == len(seq) and len(off) == len(flag) + 1
+    table = oracle.Table()
+    table.load_dump(golden.dump, p["k"])
+    names, abd, tnf = contract_features(seq, off, flag, keep, labels, table, p["k"], p["tnf_k"], p["min_length"],
+                                        p["vector_size"], p["window_size"])
+    assert names == list(golden.abd_labels) == list(golden.tnf_labels)
+    assert np.array_equal(abd, golden.abd)
+    assert np.array_equal(tnf, golden.tnf)
+
+
+def test_parser_reads_gzip_and_missing_file(tmp_path, oracle):
+    import gzip
+    import shutil
+
+    src = os.path.join(ROOT, "tests", "golden", "kat1_interleaved_10x", "reads.fq")
+    gz = tmp_path / "reads.fq.gz"
+    with open(src, "rb") as a, gzip.open(gz, "wb") as b:
+        shutil.copyfileobj(a, b)
+    plain, zipped = _lib.Fastq(src), _lib.Fastq(str(gz))
+    for x, y in zip(plain.arrays(), zipped.arrays()):
+        assert np.array_equal(x, y)
+    with pytest.raises(_lib.PgError):
+        _lib.Fastq(str(tmp_path / "nope.fq"))
+
+
+def test_parser_qualities_follow_the_sequence_layout(tmp_path):
+    (tmp_path / "i.fq").write_bytes(b"@a BX:Z:AA-1\nACGT\n+\nIII?\n@a BX:Z:AA-1\nGG\n+\n>>\n")
+    fq = _lib.Fastq(str(tmp_path / "i.fq"), want_qual=True)
+    r = fq.reads
+    q = np.ctypeslib.as_array(C.cast(r.qual, C.POINTER(C.c_uint8)), shape=(r.n_bytes,))
+    assert bytes(q) == b"III?\xff>>\xff"
+    assert bytes(fq.arrays()[0]) == b"ACGT\nGG\n"
+
+
+def test_long_lines_and_chunk_boundaries(tmp_path, oracle):
+    """Lines longer than / straddling the reader's 16 MiB chunk."""
+    rng = np.random.default_rng(3)
+    big = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(1 << 24) + 12345))
+    recs = b"".join(b"@r%d BX:Z:%s-1\n%s\n+\n%s\n" % (i, bc, s, b"I" * len(s))
+                    for i, (bc, s) in enumerate([(b"AA", big), (b"AA", b"ACGT"), (b"CC", big[:70000]), (b"CC", b"TTGA")]))
+    (tmp_path / "i.fq").write_bytes(recs)
+    fq = _lib.Fastq(str(tmp_path / "i.fq"))
+    seq, off, flag, keep = fq.arrays()
+    assert np.diff(off).tolist() == [len(big) + 1, 5, 70001, 5]
+    assert flag.tolist() == [0, 1, 0, 1] and keep.tolist() == [0, 1, 1]
+    assert bytes(seq[off[2]:off[3]]) == big[:70000] + b"\n"
