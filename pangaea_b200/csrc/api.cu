@@ -609,7 +609,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
 
     // ---- grouping --------------------------------------------------------
     {
-        Timed t(ctx, T_GROUP, 8);
+        Timed t(ctx, T_GROUP, 9); // 3 scans x 2 kernels + starts + emit + rows
         CKF(dmalloc(ctx, &gstart, (size_t)n_groups + 1));
         CKF(dmalloc(ctx, &nofeat_len, (size_t)n_groups));
         CKF(dmalloc(ctx, &d_keep, (size_t)n_groups));

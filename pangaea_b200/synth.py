@@ -34,7 +34,7 @@ def generate(n_barcodes=50, mean_pairs=20, read_len=100, n_genomes=5, genome_len
              unbarcoded_pairs=0, lower_rate=0.0):
     """-> dict(seq1, seq2 : uint8[P, L]; barcode : list[bytes] per pair ('' = none); ...)"""
     rng = np.random.default_rng(seed)
-    genomes = _LETTERS[rng.integers(0, 4, size=(n_genomes, genome_len))]
+    genomes = _LETTERS[rng.integers(0, 4, size=(n_genomes, genome_len), dtype=np.uint8)]
     abundance = rng.lognormal(0.0, 1.0, size=n_genomes)
     abundance /= abundance.sum()
     bcs = _barcodes(rng, n_barcodes, barcode_len)

@@ -1,0 +1,372 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the
+C-ABI (pangaea_b200._lib -> libpangaea_b200.so); the oracle and the golden vectors of the
+reference binaries are the checkers.  Integer results are compared bit-exactly."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+from helpers import contract_features, load_dump_arrays
+from pangaea_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(**kw):
+    return _lib.Context(**kw)
+
+
+def _names(fq, feats):
+    return [fq.label(int(g)) for g in feats.row_groups()]
+
+
+def _oracle_table_arrays(t):
+    k, v = t.items()
+    return k.astype(np.uint64), v.astype(np.uint64)
+
+
+# ------------------------------------------------------------------------------------
+# golden vectors produced by the unmodified reference binaries
+# ------------------------------------------------------------------------------------
+def test_golden_reference_outputs(golden):
+    """count_kmer / count_tnf outputs, table loaded from the same dump (`-g`)."""
+    p = golden.params
+    fq = _lib.Fastq(golden.path1, golden.reads2)
+    ctx = _ctx(k=p["k"], tnf_k=p["tnf_k"], window_size=p["window_size"], vector_size=p["vector_size"], min_length=p["min_length"])
+    keys, counts = load_dump_arrays(golden.dump, p["k"])
+    ctx.table_set(keys, counts)
+    batch = ctx.upload(fq.reads)
+    feats = ctx.featurize(batch, fq.group_keep, fq.n_groups)
+    abd, tnf = feats.raw()
+    assert _names(fq, feats) == list(golden.abd_labels) == list(golden.tnf_labels)
+    assert np.array_equal(abd, golden.abd)
+    assert np.array_equal(tnf, golden.tnf)
+
+
+def test_golden_counts_match_oracle_counter(golden, oracle):
+    """k-mer table after pg_count == the oracle's jellyfish stand-in (bit-exact counts)."""
+    if golden.name == "kat4_bins":
+        pytest.skip("hand-made dump")
+    p = golden.params
+    mq = p.get("min_qual", 0)
+    fq = _lib.Fastq(golden.path1, golden.reads2, want_qual=bool(mq))
+    ctx = _ctx(k=p["k"], min_qual_char=mq)
+    batch = ctx.upload(fq.reads)
+    ctx.count(batch)
+    keys, counts = ctx.table_export()
+    want = oracle.Table()
+    want.load_dump(golden.dump, p["k"])
+    wk, wv = _oracle_table_arrays(want)
+    assert np.array_equal(keys, wk)
+    assert np.array_equal(counts.astype(np.uint64), wv)
+    assert ctx.table_size() == len(wk)
+    # spot look-ups, in either orientation
+    probe = wk[:: max(1, len(wk) // 50)]
+    assert np.array_equal(ctx.table_get(probe).astype(np.uint64), wv[:: max(1, len(wk) // 50)])
+    rc = np.array([oracle.revcomp(int(x), p["k"]) for x in probe], dtype=np.uint64)
+    assert np.array_equal(ctx.table_get(rc).astype(np.uint64), wv[:: max(1, len(wk) // 50)])
+
+
+def test_golden_whole_path_from_host_buffers(golden, oracle):
+    """pg_extract_features (count + featurize + normalize) vs oracle over the same files."""
+    if golden.name == "kat4_bins":
+        pytest.skip("hand-made dump")
+    p = golden.params
+    mq = p.get("min_qual", 0)
+    fq = _lib.Fastq(golden.path1, golden.reads2, want_qual=bool(mq))
+    ctx = _ctx(k=p["k"], tnf_k=p["tnf_k"], window_size=p["window_size"], vector_size=p["vector_size"],
+               min_length=p["min_length"], min_qual_char=mq)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    abd, tnf = feats.raw()
+    assert _names(fq, feats) == list(golden.abd_labels)
+    assert np.array_equal(abd, golden.abd) and np.array_equal(tnf, golden.tnf)
+    a, t, w = feats.normalized()
+    oa, ot, ow = oracle.data_init(golden.abd, golden.tnf)
+    assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+
+
+# ------------------------------------------------------------------------------------
+# seeded random inputs vs the oracle
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,mode", [(15, _lib.PG_TABLE_AUTO), (11, _lib.PG_TABLE_AUTO), (12, _lib.PG_TABLE_AUTO), (14, _lib.PG_TABLE_AUTO),
+                                    (16, _lib.PG_TABLE_AUTO), (15, _lib.PG_TABLE_HASH), (21, _lib.PG_TABLE_AUTO), (31, _lib.PG_TABLE_AUTO),
+                                    (1, _lib.PG_TABLE_AUTO), (7, _lib.PG_TABLE_HASH)])
+def test_random_vs_oracle(tmp_path, oracle, k, mode):
+    data = synth.generate(n_barcodes=60, mean_pairs=12, read_len=100, n_genomes=3, genome_len=40_000, frag_len=6_000,
+                          seed=100 + k, unbarcoded_pairs=9, n_rate=0.004, lower_rate=0.003)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None, k=k, tnf_k=4, mlen=1500, vs=50, ws=2)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(k=k, window_size=2, vector_size=50, min_length=1500, table_mode=mode, table_capacity=1 << 18 if (mode == _lib.PG_TABLE_HASH or k > 16) else 0)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    g_abd, g_tnf = feats.raw()
+    assert _names(fq, feats) == list(names)
+    assert np.array_equal(g_tnf, tnf)
+    assert np.array_equal(g_abd, abd)
+    keys, counts = ctx.table_export()
+    wk, wv = _oracle_table_arrays(oracle.count_fastq(path, k))
+    assert np.array_equal(keys, wk) and np.array_equal(counts.astype(np.uint64), wv)
+
+
+@pytest.mark.parametrize("tnf_k", [1, 2, 3, 5, 6])
+def test_tnf_k_variants(tmp_path, oracle, tnf_k):
+    data = synth.generate(n_barcodes=12, mean_pairs=10, read_len=80, seed=7 + tnf_k, n_rate=0.01)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    names, tnf = oracle.tnf(path, None, tnf_k, 0)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(k=9, tnf_k=tnf_k, min_length=0)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    assert _names(fq, feats) == list(names)
+    assert np.array_equal(feats.raw()[1], tnf)
+
+
+def test_tiny_clouds_overflow_the_slots(tmp_path, oracle):
+    """One pair per barcode (the hybrid 'per-read' shape): dozens of clouds per tile, so the
+    block-private slots overflow into direct global reductions."""
+    data = synth.generate(n_barcodes=700, mean_pairs=1, read_len=150, n_genomes=2, genome_len=30_000, frag_len=3_000, seed=5)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None, k=15, mlen=0)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(min_length=0)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    assert _names(fq, feats) == list(names)
+    g_abd, g_tnf = feats.raw()
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+
+
+def test_ragged_lengths_and_long_reads(tmp_path, oracle):
+    rng = np.random.default_rng(8)
+    recs = []
+    for i in range(400):
+        bc = b"ACGT"[i // 100:i // 100 + 1] * 8
+        for _ in range(2):
+            n = int(rng.choice([0, 1, 14, 15, 16, 17, 31, 32, 33, 47, 64, 65, 100, 1000, 5000]))
+            s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n, p=[.245, .245, .245, .245, .02]))
+            recs.append(b"@r%d BX:Z:%s-1\n%s\n+\n%s\n" % (i, bc, s, b"I" * n))
+    path = str(tmp_path / "i.fq")
+    open(path, "wb").write(b"".join(recs))
+    names, abd, tnf = oracle.featurize(path, None, k=15, mlen=2000)
+    fq = _lib.Fastq(path)
+    ctx = _ctx()
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    assert _names(fq, feats) == list(names) and len(names) >= 3
+    g_abd, g_tnf = feats.raw()
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+
+
+def test_homopolymers_and_repeats(tmp_path, oracle):
+    """Poly-G tails / tandem repeats: many identical consecutive k-mers (run merging in the
+    count kernel) and counts far above window*vector (ignored bins)."""
+    recs = []
+    for i in range(60):
+        bc = b"AAAA" if i < 30 else b"CCCC"
+        for s in (b"G" * 120, b"ACGTACGTAC" * 12 + b"T" * 30):
+            recs.append(b"@r%d BX:Z:%s-1\n%s\n+\n%s\n" % (i, bc, s, b"I" * len(s)))
+    path = str(tmp_path / "i.fq")
+    open(path, "wb").write(b"".join(recs))
+    names, abd, tnf = oracle.featurize(path, None, k=15, mlen=100, vs=400, ws=10)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(min_length=100)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    g_abd, g_tnf = feats.raw()
+    assert _names(fq, feats) == list(names)
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    key = oracle.canonical(oracle.encode("G" * 15), 15)
+    assert ctx.table_get(np.array([key], dtype=np.uint64))[0] == 60 * 106
+
+
+def test_empty_and_degenerate_batches():
+    ctx = _ctx(min_length=0)
+    # nothing at all
+    r = _lib.make_reads(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8))
+    feats = ctx.extract_features(r, np.zeros(1, np.uint8))
+    assert feats.rows == 0 and feats.raw()[0].shape == (0, 400)
+    assert feats.normalized()[2].shape == (0,)
+    # a single all-N pair carrying a change flag: cloud 0 holds it, cloud 1 is empty
+    seq = np.frombuffer(b"NNNNNNNNNNNNNNNNNNNN\nNNNNNNNNNNNNNNNNNNNN\n", dtype=np.uint8)
+    r = _lib.make_reads(seq, np.array([0, 21, 42], np.int64), np.array([0, 1], np.uint8))
+    feats = ctx.extract_features(r, np.array([1, 1], np.uint8))
+    assert feats.rows == 1 and feats.row_groups().tolist() == [0]
+    abd, tnf = feats.raw()
+    assert abd.sum() == 0 and tnf.sum() == 0
+    a, t, w = feats.normalized()
+    assert not a.any() and not t.any() and w.tolist() == [0.0]  # zero rows stay zero (sklearn zero-norm rule)
+    assert ctx.table_size() == 0
+    # wrong n_groups is an error, not a crash
+    with pytest.raises(_lib.PgError, match="n_groups"):
+        ctx.extract_features(r, np.array([1, 1, 1], np.uint8))
+    # featurize before any count
+    ctx2 = _ctx()
+    b = ctx2.upload(r)
+    with pytest.raises(_lib.PgError, match="table is empty"):
+        ctx2.featurize(b, np.array([1, 1], np.uint8))
+
+
+def test_negative_min_length_drops_everything(tmp_path):
+    """`reads_seq.size() <= mlen` is unsigned in the reference: -l -1 emits nothing."""
+    data = synth.generate(n_barcodes=5, mean_pairs=5, read_len=50, seed=1)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(min_length=-1)
+    assert ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups).rows == 0
+
+
+def test_hash_table_full_is_reported(tmp_path):
+    data = synth.generate(n_barcodes=30, mean_pairs=20, read_len=100, seed=2)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(k=21, table_capacity=1 << 10)
+    with pytest.raises(_lib.PgError, match="full"):
+        ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+
+
+def test_table_set_semantics(oracle):
+    """kmer2frequency[key] = freq (count_kmer.cpp:166): re-canonicalised, last one wins."""
+    ctx = _ctx(k=15)
+    a = oracle.encode("ACGTTGCAACGTACG")
+    rc = oracle.revcomp(a, 15)
+    ctx.table_set(np.array([a, rc, 5], np.uint64), np.array([7, 9, 3], np.uint32))
+    assert ctx.table_get(np.array([a, rc, 5, 6], np.uint64)).tolist() == [9, 9, 3, 0]
+    keys, counts = ctx.table_export()
+    assert keys.tolist() == sorted([oracle.canonical(a, 15), oracle.canonical(5, 15)])
+    ctx.table_clear()
+    assert ctx.table_size() == 0
+
+
+# ------------------------------------------------------------------------------------
+# Data.__init__ and the zero-copy hand-off
+# ------------------------------------------------------------------------------------
+def test_normalize_bit_exact_vs_sklearn_semantics(oracle):
+    rng = np.random.default_rng(4)
+    abd = rng.integers(0, 3000, size=(1000, 400)).astype(np.int64) * (rng.random((1000, 400)) < 0.05)
+    abd[17] = 0
+    abd[18, 3] = 4_000_000_000  # near the u32 ceiling
+    tnf = rng.integers(0, 5000, size=(1000, 136)).astype(np.int64)
+    ctx = _ctx()
+    f = ctx.features_from_raw(abd, tnf)
+    a, t, w = f.normalized()
+    oa, ot, ow = oracle.data_init(abd, tnf)
+    assert a.dtype == np.float32 and w.dtype == np.float64
+    assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+
+
+def test_dlpack_zero_copy_to_torch(tmp_path):
+    import torch
+
+    data = synth.generate(n_barcodes=20, mean_pairs=15, read_len=100, seed=3)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(min_length=0)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    a, t, w = feats.normalized()
+    ta, tt, tw, ra = feats.torch(_lib.ABD), feats.torch(_lib.TNF), feats.torch(_lib.WEIGHTS), feats.torch(_lib.ABD_RAW)
+    assert ta.is_cuda and ta.dtype == torch.float32 and tuple(ta.shape) == a.shape
+    assert tw.dtype == torch.float64 and ra.dtype == torch.int32
+    assert ta.data_ptr() == _lib.lib().pg_features_device_ptr(feats.h, _lib.ABD)  # same memory, no copy
+    assert np.array_equal(ta.cpu().numpy(), a) and np.array_equal(tt.cpu().numpy(), t) and np.array_equal(tw.cpu().numpy(), w)
+    feats.free()  # the tensors keep the buffers alive
+    del ctx
+    assert np.array_equal(ta.cpu().numpy(), a)
+    x = torch.nn.functional.softmax(ta, dim=1)  # usable by an unchanged torch consumer
+    assert torch.isfinite(x).all()
+
+
+# ------------------------------------------------------------------------------------
+# the drop-in classes
+# ------------------------------------------------------------------------------------
+def _args(out, **kw):
+    d = dict(tnf_kmer=4, window_size=10, vector_size=400, kmer=15, min_length=2000, threads=4, output=str(out),
+             reads1=None, reads2=None, interleaved_reads=None)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_feature_and_data_drop_in(tmp_path, oracle):
+    from pangaea_b200 import Data, Feature
+
+    data = synth.generate(n_barcodes=40, mean_pairs=20, read_len=100, n_genomes=3, genome_len=50_000, frag_len=8_000, seed=21,
+                          unbarcoded_pairs=4)
+    path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    ft = Feature(_args(tmp_path, interleaved_reads=path), script_path="unused")
+    g_names, g_abd, g_tnf = ft.extract_features()
+    assert g_abd.dtype == np.int64 and g_abd.shape == abd.shape
+    assert list(g_names) == list(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    fd = tmp_path / "1.features"
+    assert (fd / "feature_finished").read_text() == "feature finished"
+    assert (fd / "abundance.k15.v400.w10.m2000.pkl").exists() and (fd / "tnf.m2000.pkl").exists()
+    l_names, l_abd, l_tnf = Feature(_args(tmp_path, interleaved_reads=path), "unused").load_features()
+    assert list(l_names) == list(names) and np.array_equal(l_abd, abd) and np.array_equal(l_tnf, tnf)
+
+    oa, ot, ow = oracle.data_init(abd, tnf)
+    for ds in (Data(g_names, g_abd, g_tnf), Data(g_names, g_abd, g_tnf, features=ft.features)):
+        assert len(ds) == len(names)
+        assert np.array_equal(ds.abd, oa) and np.array_equal(ds.tnf, ot) and np.array_equal(ds.weights, ow)
+        item = ds[3]
+        assert set(item) == {"abd", "tnf", "bc"} and item["bc"] == names[3]
+        assert ds.abd_cuda.is_cuda and np.array_equal(ds.abd_cuda.cpu().numpy(), oa)
+    with pytest.raises(ValueError):
+        Feature(_args(tmp_path / "x"), "unused").extract_features()
+
+
+def test_feature_paired_mode_uses_min_qual(tmp_path, oracle):
+    from conftest import GoldenCase
+    from pangaea_b200 import Feature
+
+    g = GoldenCase("synth_paired_minqual")
+    p = g.params
+    ft = Feature(_args(tmp_path, reads1=g.reads1, reads2=g.reads2, min_length=p["min_length"]), "unused")
+    names, abd, tnf = ft.extract_features(write_cache=False)
+    assert list(names) == list(g.abd_labels) and np.array_equal(abd, g.abd) and np.array_equal(tnf, g.tnf)
+
+
+# ------------------------------------------------------------------------------------
+# size-independent properties at a larger size (device-generated reads)
+# ------------------------------------------------------------------------------------
+def test_properties_at_scale():
+    import torch
+
+    from bench import make_synthetic_batch  # same generator the benchmark uses
+
+    n_pairs, L = 400_000, 100
+    ctx = _ctx()
+    s = make_synthetic_batch(ctx, n_pairs=n_pairs, read_len=L, n_barcodes=4000, n_genomes=8, genome_len=300_000, seed=9)
+    batch = ctx.adopt(s["reads"], keepalive=s)
+    ctx.count(batch)
+    # (1) counters sum to the number of valid windows (every window is counted exactly once)
+    seq = s["seq"].cpu().numpy().reshape(2 * n_pairs, L + 1)[:, :L]
+    valid = np.isin(seq, np.frombuffer(b"ACGT", dtype=np.uint8))
+    def windows(k):
+        c = np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)
+        return int(((c[:, k:] - c[:, :-k]) == k).sum())
+    table = ctx.table_as_torch()
+    assert int(table.to(torch.int64).sum()) == windows(15)
+    # (2) featurize: TNF row sums = 4-mer windows of the emitted clouds; deterministic; linear in the table
+    keep = np.ones(s["n_groups"], np.uint8)
+    keep[0] = 0
+    f1 = ctx.featurize(batch, keep)
+    f2 = ctx.featurize(batch, keep)
+    a1, t1 = f1.raw()
+    a2, t2 = f2.raw()
+    assert np.array_equal(a1, a2) and np.array_equal(t1, t2)
+    assert f1.rows > 3000
+    groups = f1.row_groups()
+    per_read4 = ((np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, 4:]
+                  - np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, :-4]) == 4).sum(axis=1)
+    flags = s["flag"].cpu().numpy()
+    gid = np.concatenate([[0], np.cumsum(flags & 1)[:-1]])
+    want = np.bincount(gid, weights=per_read4, minlength=s["n_groups"]).astype(np.int64)
+    assert np.array_equal(t1.sum(axis=1), want[groups])
+    # every look-up finds its k-mer (count >= 1) and almost all land inside the 400 bins
+    per_read15 = ((np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, 15:]
+                   - np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, :-15]) == 15).sum(axis=1)
+    want15 = np.bincount(gid, weights=per_read15, minlength=s["n_groups"]).astype(np.int64)
+    assert np.array_equal(a1.sum(axis=1), want15[groups])  # no count reaches 4000 at this depth
+    # (3) counting the batch a second time doubles every counter: bins shift accordingly
+    ctx.count(batch)
+    assert int(ctx.table_as_torch().to(torch.int64).sum()) == 2 * windows(15)
+    # (4) normalised rows sum to 1, weights in (0, 1]
+    a, t, w = f1.normalized()
+    assert np.allclose(a.sum(axis=1), 1, atol=1e-5) and np.allclose(t.sum(axis=1), 1, atol=1e-5)
+    assert (w > 0).all() and (w <= 1).all()
