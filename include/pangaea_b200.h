@@ -110,7 +110,8 @@ int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE fl
 int pg_count(pg_ctx* ctx, pg_batch* b);
 int pg_table_clear(pg_ctx* ctx);
 /* kmer2frequency[key] = count (count_kmer.cpp:166): assignment, keys in the reference's
- * canonical form or not (re-canonicalised).  count 0 is stored as "absent". */
+ * canonical form or not (re-canonicalised).  A key set with count 0 is PRESENT with
+ * frequency 0 (lands in bin 0), as in the reference; pg_table_get cannot tell it from absent. */
 int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* counts, int64_t n);
 int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* counts_out, int64_t n);
 /* number of distinct k-mers; then export (key = reference canonical form, ascending) */

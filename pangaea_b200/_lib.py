@@ -120,6 +120,7 @@ def make_reads(seq, read_off, read_flag, qual=None, n_reads=None, n_bytes=None) 
     r.seq, r.qual, r.read_off, r.read_flag = _ptr(seq), _ptr(qual), _ptr(read_off), _ptr(read_flag)
     r.n_reads = int(n_reads if n_reads is not None else len(read_flag))
     r.n_bytes = int(n_bytes if n_bytes is not None else len(seq))
+    r._keepalive = (seq, qual, read_off, read_flag)  # the struct only holds raw addresses
     return r
 
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ int64_t advance_group(const int64_t* __restrict__ gst
 
 __device__ __forceinline__ uint32_t abd_bin(const FeatParams& P, uint32_t c)
 {
-    // int pos = count / bin_size  (count_kmer.cpp:90); caller guarantees 0 < c < clamp
+    // int pos = count / bin_size  (count_kmer.cpp:90); caller guarantees c < clamp
     return P.use_magic ? (uint32_t)(((uint64_t)c * P.magic) >> 32) : c / P.ws;
 }
 
@@ -84,7 +84,7 @@ __device__ __forceinline__ void feat_one(const FeatParams& P, uint64_t lo, uint6
         const uint64_t w = win & low_mask64(2 * k);
         uint32_t c = MODE == kDense ? __ldg(P.table.counts + dense_index_of_window((uint32_t)w, k))
                                     : table_get_hash(P.table, canonical_of_window(w, k));
-        if (c != 0u && c < P.clamp) atomicAdd(abd_row + abd_bin(P, c), 1u);
+        if (c != 0u && (c & kCountMask) < P.clamp) atomicAdd(abd_row + abd_bin(P, c & kCountMask), 1u);
     }
 }
 
@@ -168,8 +168,10 @@ featurize_kernel(const FeatParams P)
                         uint32_t cur = 0xFFFFFFFFu, run = 0u;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const uint32_t c = cnt[i];
-                            if (c == 0u || c >= P.clamp) continue;
+                            uint32_t c = cnt[i];
+                            if (c == 0u) continue; // absent from the table (count_kmer.cpp:87)
+                            c &= kCountMask;
+                            if (c >= P.clamp) continue;
                             const uint32_t b = abd_bin(P, c);
                             if (b == cur) { ++run; continue; }
                             if (run) atomicAdd(abd_row + cur, run);

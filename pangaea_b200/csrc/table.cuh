@@ -18,6 +18,11 @@
 namespace pg {
 
 constexpr uint64_t kEmptyKey = ~0ull;
+// A dump line "KMER\t0" makes the k-mer PRESENT with frequency 0 in the reference
+// (count_kmer.cpp:166 then :87-93 -> bin 0).  jellyfish never writes such a line, but
+// pg_table_set honours it: the entry is stored as this marker, and readers mask it off.
+constexpr uint32_t kPresentZero = 0x80000000u;
+constexpr uint32_t kCountMask = 0x7FFFFFFFu;
 enum TableMode { kDense = 0, kHash = 1 };
 
 struct TableView {
@@ -69,13 +74,13 @@ __global__ void table_set_kernel(TableView t, int mode, const uint64_t* __restri
     if (i >= n) return;
     uint64_t v = keys[i] & low_mask64(2 * t.k);
     if (mode == kDense) {
-        t.counts[dense_index_of_fwd(v, t.k)] = counts[i];
+        t.counts[dense_index_of_fwd(v, t.k)] = counts[i] ? counts[i] : kPresentZero;
     } else {
         uint64_t key = canonical_of_fwd(v, t.k);
         uint64_t slot = mix64(key) & t.capacity_mask;
         for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
             unsigned long long cur = atomicCAS(t.keys + slot, kEmptyKey, (unsigned long long)key);
-            if (cur == kEmptyKey || cur == key) { t.counts[slot] = counts[i]; return; }
+            if (cur == kEmptyKey || cur == key) { t.counts[slot] = counts[i] ? counts[i] : kPresentZero; return; }
             slot = (slot + 1) & t.capacity_mask;
         }
         *t.overflow = 1u;
@@ -87,7 +92,7 @@ __global__ void table_get_kernel(TableView t, int mode, const uint64_t* __restri
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t v = keys[i] & low_mask64(2 * t.k);
-    out[i] = mode == kDense ? t.counts[dense_index_of_fwd(v, t.k)] : table_get_hash(t, canonical_of_fwd(v, t.k));
+    out[i] = (mode == kDense ? t.counts[dense_index_of_fwd(v, t.k)] : table_get_hash(t, canonical_of_fwd(v, t.k))) & kCountMask;
 }
 
 // number of non-zero counters (distinct k-mers)
@@ -112,7 +117,7 @@ __global__ void table_export_kernel(TableView t, int mode, uint64_t n_slots, uin
         unsigned long long at = atomicAdd(cursor, 1ull);
         if (at < cap) {
             keys_out[at] = mode == kDense ? key_of_dense_index(i, t.k) : (uint64_t)t.keys[i];
-            counts_out[at] = c;
+            counts_out[at] = c & kCountMask;
         }
     }
 }

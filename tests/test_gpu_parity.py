@@ -355,7 +355,7 @@ def test_properties_at_scale():
     per_read4 = ((np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, 4:]
                   - np.cumsum(np.concatenate([np.zeros((valid.shape[0], 1), int), valid], axis=1), axis=1)[:, :-4]) == 4).sum(axis=1)
     flags = s["flag"].cpu().numpy()
-    gid = np.concatenate([[0], np.cumsum(flags & 1)[:-1]])
+    gid = np.concatenate([[0], np.cumsum(flags & 1)[:-1]]).astype(np.int64)
     want = np.bincount(gid, weights=per_read4, minlength=s["n_groups"]).astype(np.int64)
     assert np.array_equal(t1.sum(axis=1), want[groups])
     # every look-up finds its k-mer (count >= 1) and almost all land inside the 400 bins
