@@ -192,14 +192,28 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # algorithmic bytes (DESIGN.md "Roofline")
 # --------------------------------------------------------------------------------------
-def algorithmic_bytes(n_bytes, windows_count, windows_feat, rows, vs=400, td=136):
-    stream = 0.25 + 0.125  # 2-bit codes + 1 validity bit per base position
-    return {
-        "pack": n_bytes * (1.0 + 0.25 + 2 * 0.125),
-        "count": n_bytes * stream + 8.0 * windows_count,         # u32 counter read-modify-write per window
-        "featurize": n_bytes * stream + 4.0 * windows_feat + 4.0 * rows * (vs + td),
-        "normalize": 2 * 4.0 * rows * (vs + td),
-    }
+def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows, sliced, vs=400, td=136):
+    """Bytes each kernel has to move by design (DESIGN.md "Kernels and rooflines").  stream =
+    2-bit codes + 1 validity bit per base position.  With the L2-sliced table (k = 15) a pass is
+    two kernels: scatter writes one entry per window, apply reads it back and touches the counter."""
+    stream = 0.25 + 0.125
+    out = 4.0 * rows * (vs + td)
+    b = {"pack": n_bytes * (1.0 + 0.25 + 2 * 0.125), "normalize": 2 * out}
+    if sliced:
+        b["count_scatter"] = n_bytes * stream + 4.0 * entries_count
+        b["count_apply"] = 4.0 * entries_count + 8.0 * windows_count      # u32 counter read-modify-write per window
+        b["feat_scatter"] = n_bytes * stream + 8.0 * windows_feat
+        b["feat_apply"] = 8.0 * windows_feat + 4.0 * windows_feat + out   # entry + u32 counter read per window, tallies out
+    else:
+        b["count_apply"] = n_bytes * stream + 8.0 * windows_count
+        b["feat_apply"] = n_bytes * stream + 4.0 * windows_feat + out
+    return b
+
+
+KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_count_kernel", "count_apply": "bucket_apply_count_kernel",
+                   "group": "flag_count/tile_scan/group_starts/row_assign kernels", "feat_scatter": "bucket_scatter_feat_kernel",
+                   "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
+STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_apply", 1), ("group", 2), ("feat_scatter", 7), ("feat_apply", 3), ("normalize", 4))
 
 
 def load_peaks():
@@ -301,7 +315,8 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    stage_ms = {n: ctx.timing(w)[0] / args.steps for n, w in (("pack", 0), ("count", 1), ("group", 2), ("featurize", 3), ("normalize", 4))}
+    stage_ms = {n: ctx.timing(w)[0] / args.steps for n, w in STAGE_SLOTS}
+    stage_launches = {n: ctx.timing(w)[1] // args.steps for n, w in STAGE_SLOTS}
     launches = ctx.timing(_lib.T_ALL)[1]
 
     t = torch.tensor([wall_ms, dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -321,17 +336,23 @@ def main():
     f.free()
     if windows_count is None:
         windows_count = windows_feat
-    alg = algorithmic_bytes(batch_data["n_bytes"], windows_count, windows_feat, rows)
+    sliced = stage_ms["count_scatter"] > 0
+    alg = algorithmic_bytes(batch_data["n_bytes"], windows_count, windows_count, windows_feat, rows, sliced)
     peak, peak_src = load_peaks()
-    dom = max(("count", "featurize"), key=lambda n: stage_ms[n])
-    kname = {"count": "count_kernel", "featurize": "featurize_kernel"}[dom]
+    dom = max((n for n in alg if n in stage_ms), key=lambda n: stage_ms[n])
+    kname = KERNEL_OF_STAGE[dom] if sliced else {"count_apply": "count_kernel", "feat_apply": "featurize_kernel"}.get(dom, KERNEL_OF_STAGE[dom])
+    n_launch = max(1, stage_launches[dom] - (stage_launches[dom] // 2 if dom.endswith("scatter") else 0))  # scatter spans include the reset kernel
     achieved = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
+    b_pair = 2456.0 if args.read_len == 100 else 3832.0
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": load_traffic().get(kname), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg[dom]),
-                "ms_per_launch": round(stage_ms[dom], 3),
+                "traffic": load_traffic().get(kname), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg[dom] / n_launch), "launches_per_step": n_launch,
+                "ms_per_launch": round(stage_ms[dom] / n_launch, 3),
                 "stages_ms": {k: round(v, 3) for k, v in stage_ms.items()},
-                "stages_GBps": {k: round(alg[k] / (stage_ms[k] / 1e3) / 1e9, 1) for k in alg if stage_ms[k] > 0},
-                "path_frac_of_B(L)": round((2456.0 if args.read_len == 100 else 3832.0) * (value / world / 2) / (peak * 1e9), 4)}
+                "stages_GBps": {k: round(alg[k] / (stage_ms[k] / 1e3) / 1e9, 1) for k in alg if stage_ms.get(k, 0) > 0},
+                "whole_path": {"B_per_pair": b_pair, "achieved_GBps": round(b_pair * (value / world / 2) / 1e9, 1),
+                               "frac": round(b_pair * (value / world / 2) / (peak * 1e9), 4),
+                               "note": "SURVEY.md §8d algorithmic bytes per pair x pairs/s per GPU / measured HBM copy bandwidth"}}
 
     # ---- e2e: host buffers through the C-ABI ----
     e2e = None

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpangaea_b200.so")
 
 PG_READ_CHANGE, PG_READ_NOFEAT = 1, 2
 PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH = 0, 1, 2
-T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL = range(6)
+T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL, T_COUNT_SCATTER, T_FEAT_SCATTER = range(8)
 ABD_RAW, TNF_RAW, ABD, TNF, WEIGHTS = range(5)
 
 
@@ -319,6 +319,7 @@ class Context:
         """The dense counter array as an int32 CUDA tensor sharing memory (for all_reduce)."""
         import torch
 
+        self.synchronize()  # the ctx stream is non-blocking: torch's stream is not ordered after it
         ptr, n = self.table_dense_view()
 
         class _Arr:

@@ -2,6 +2,7 @@
 // Host orchestration only: allocation, launches, read-backs.  No CPU compute path.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -10,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/pangaea_b200.h"
+#include "bucket.cuh"
 #include "count.cuh"
 #include "featurize.cuh"
 #include "kmer.cuh"
@@ -24,7 +26,8 @@ using namespace pg;
 // ---------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------
-enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5 };
+// timing slots: one per kernel family (pg_timing_get `which`)
+enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_SLOTS = 8 };
 
 struct pg_ctx {
     pg_params p;
@@ -43,12 +46,17 @@ struct pg_ctx {
     // pinned read-back scratch
     int64_t* h_pin = nullptr;
     int64_t* d_scalar = nullptr; // 8 x int64 device scalars
+    BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
+    double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
+    bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
+    int64_t seg_words = 1ll << 25; // words per segment of the L2-sliced path: 2^30 windows -> entry buffer <= 4 GiB (count) /
+                                   // 8 GiB (featurize); PG_SEG_WORDS overrides (tests force many segments on small inputs)
     std::string err;
     // timing
     struct Span { int which; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
-    int64_t launches[5] = { 0, 0, 0, 0, 0 };
+    int64_t launches[T_SLOTS] = { 0 };
 };
 
 struct pg_batch {
@@ -235,6 +243,10 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaMalloc((void**)&ctx->d_overflow, sizeof(uint32_t)));
     CKC(cudaMemset(ctx->d_overflow, 0, sizeof(uint32_t)));
     CKC(cudaMalloc((void**)&ctx->d_scalar, 8 * sizeof(int64_t)));
+    CKC(cudaMalloc((void**)&ctx->d_bucket, sizeof(BucketState)));
+    { const char* e = getenv("PG_REGION_SLACK"); if (e && atof(e) > 0) ctx->region_slack = atof(e); }
+    { const char* e = getenv("PG_FORCE_DIRECT"); ctx->force_direct = e && e[0] == '1'; }
+    { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= kTileWords) ctx->seg_words = atoll(e) / kTileWords * kTileWords; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
         ctx->n_slots = dense_entries(p->k);
@@ -246,6 +258,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     }
     CKC(cudaFuncSetAttribute(featurize_kernel<kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaFuncSetAttribute(featurize_kernel<kHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
 #undef CKC
     *out = ctx;
@@ -259,7 +272,7 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
-    cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar);
+    cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -290,7 +303,7 @@ extern "C" int pg_timing_reset(pg_ctx* ctx)
 
 extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* launches_out)
 {
-    if (!ctx || which < 0 || which > T_ALL) return fail(ctx, PG_ERR_INVALID, "pg_timing_get: bad argument");
+    if (!ctx || which < 0 || which >= T_SLOTS) return fail(ctx, PG_ERR_INVALID, "pg_timing_get: bad argument");
     CK(cudaStreamSynchronize(ctx->stream));
     double ms = 0;
     int64_t n = 0;
@@ -300,7 +313,7 @@ extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* la
             CK(cudaEventElapsedTime(&t, s.a, s.b));
             ms += t;
         }
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < T_SLOTS; ++i)
         if (which == T_ALL || i == which) n += ctx->launches[i];
     if (ms_out) *ms_out = ms;
     if (launches_out) *launches_out = n;
@@ -433,13 +446,59 @@ static int check_overflow(pg_ctx* ctx)
     return PG_OK;
 }
 
+// the dense table is swept slice by slice when it is much larger than L2 (bucket.cuh)
+static bool use_buckets(const pg_ctx* c)
+{
+    if (c->mode != kDense || c->force_direct) return false;
+    const uint64_t nb = c->n_slots >> kSliceBits;
+    return nb >= 2 && nb <= (uint64_t)kMaxBuckets;
+}
+
+static BucketGeom bucket_geom(const pg_ctx* ctx, int64_t seg_words)
+{
+    BucketGeom geo;
+    geo.n_buckets = (int)(ctx->n_slots >> kSliceBits);
+    geo.low_mask = (1u << kSliceBits) - 1u;
+    const double mean = (double)seg_words * 32.0 / geo.n_buckets;
+    geo.cap = std::max<unsigned long long>(32ull, (((unsigned long long)(mean * ctx->region_slack) + 31ull) / 32ull) * 32ull);
+    return geo;
+}
+
+static int count_bucketed(pg_ctx* ctx, pg_batch* b)
+{
+    const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
+    const BucketGeom geo = bucket_geom(ctx, seg_words);
+    uint32_t* entries;
+    CK(dmalloc(ctx, &entries, (size_t)geo.cap * geo.n_buckets));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_count_kernel, 256, 0));
+    for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
+        const int64_t w1 = std::min(b->n_words, w0 + seg_words);
+        const int64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
+        {
+            Timed t(ctx, T_COUNT_SCATTER, 2);
+            bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
+            bucket_scatter_count_kernel<<<(int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ), 256, 0, ctx->stream>>>(
+                b->codes, b->maskC, w0, w1, ctx->p.k, geo, ctx->d_bucket, entries, ctx->counts);
+        }
+        Timed t(ctx, T_COUNT, 1);
+        bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
+    }
+    CK(cudaGetLastError());
+    dfree(ctx, entries);
+    return PG_OK;
+}
+
 extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
 {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
     int rc = ensure_table(ctx, b->n_bytes);
     if (rc) return rc;
-    if (b->n_words) {
+    if (b->n_words && use_buckets(ctx)) {
+        rc = count_bucketed(ctx, b);
+        if (rc) return rc;
+    } else if (b->n_words) {
         Timed t(ctx, T_COUNT, 1);
         const int grid = grid_for(b->n_words, 256, ctx->sm_count * 8);
         if (ctx->mode == kDense) count_kernel<kDense><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, b->n_words, view(ctx));
@@ -587,6 +646,8 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     CK(cudaSetDevice(ctx->p.device));
 
     int64_t* gstart = nullptr;
+    uint32_t* maskR = nullptr;
+    unsigned long long* feat_entries = nullptr;
     unsigned long long* nofeat_len = nullptr;
     uint8_t *d_keep = nullptr, *emit = nullptr;
     int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr;
@@ -595,7 +656,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     pg_features* f = nullptr;
     auto cleanup = [&]() {
         dfree(ctx, gstart); dfree(ctx, nofeat_len); dfree(ctx, d_keep); dfree(ctx, emit);
-        dfree(ctx, row_of_group); dfree(ctx, group_of_row_full);
+        dfree(ctx, row_of_group); dfree(ctx, group_of_row_full); dfree(ctx, maskR); dfree(ctx, feat_entries);
     };
 #define CKF(call)                                                                                        \
     do {                                                                                                 \
@@ -609,7 +670,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
 
     // ---- grouping --------------------------------------------------------
     {
-        Timed t(ctx, T_GROUP, 9); // 3 scans x 2 kernels + starts + emit + rows
+        Timed t(ctx, T_GROUP, 10); // 3 scans x 2 kernels + starts + emit + rows + dropped-cloud mask
         CKF(dmalloc(ctx, &gstart, (size_t)n_groups + 1));
         CKF(dmalloc(ctx, &nofeat_len, (size_t)n_groups));
         CKF(dmalloc(ctx, &d_keep, (size_t)n_groups));
@@ -618,13 +679,16 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
         CKF(dmalloc(ctx, &group_of_row_full, (size_t)n_groups));
         CKF(cudaMemsetAsync(nofeat_len, 0, (size_t)n_groups * sizeof(unsigned long long), ctx->stream));
         CKF(cudaMemcpyAsync(d_keep, group_keep, (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
+        // working copy of the feature mask: NOFEAT reads and dropped clouds get cleared in it
+        CKF(dmalloc(ctx, &maskR, (size_t)b->n_words + 2));
+        CKF(cudaMemcpyAsync(maskR, b->maskF, ((size_t)b->n_words + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 
         // PG_READ_NOFEAT reads are rare; when present their bases are masked out of maskF
         rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_NOFEAT, &tile_off, &nofeat);
         if (rc) { cleanup(); return rc; }
         dfree(ctx, tile_off);
         if (nofeat)
-            clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, b->maskF);
+            clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, maskR);
 
         rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_CHANGE, &tile_off, &changes);
         if (rc) { cleanup(); return rc; }
@@ -651,6 +715,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
             row_assign_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(emit, n_groups, tile_off, row_of_group, group_of_row_full);
         }
         dfree(ctx, tile_off);
+        clear_dropped_groups_kernel<<<(int)std::min<int64_t>(n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(gstart, row_of_group, n_groups, maskR);
         CKF(cudaGetLastError());
     }
 
@@ -670,7 +735,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     // ---- the pass over the bases -------------------------------------------
     if (rows && b->n_words) {
         FeatParams P;
-        P.codes = b->codes; P.maskF = b->maskF; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
+        P.codes = b->codes; P.maskF = maskR; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
         P.gstart = gstart; P.n_groups = n_groups; P.row_of_group = row_of_group;
         P.tnf_k = ctx->p.tnf_k; P.vs = f->vs; P.td = f->td;
         P.ws = (uint32_t)ctx->p.window_size;
@@ -682,6 +747,34 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
         P.lut = ctx->d_lut;
         P.abd = f->abd_raw; P.tnf = f->tnf_raw;
         P.table = view(ctx);
+        if (use_buckets(ctx)) {
+            // ---- L2-sliced path: TNF + partition of (index, row) pairs, then slice-by-slice look-ups ----
+            const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
+            const BucketGeom geo = bucket_geom(ctx, seg_words);
+            CKF(dmalloc(ctx, &feat_entries, (size_t)geo.cap * geo.n_buckets));
+            const size_t smem_s = (size_t)2 * kTileEntries * sizeof(uint32_t) + (size_t)kSlots * P.td * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
+            int occ_s = 1;
+            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, bucket_scatter_feat_kernel, 256, smem_s));
+            if (occ_s < 1) { cleanup(); pg_features_free(ctx, f); return fail(ctx, PG_ERR_INVALID, "tnf_k too large for shared memory"); }
+            for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
+                const int64_t w1 = std::min(b->n_words, w0 + seg_words);
+                const int64_t n_cta = std::min<int64_t>((int64_t)ctx->sm_count * occ_s, (w1 - w0 + kTileWords - 1) / kTileWords);
+                int64_t wpc = (w1 - w0 + n_cta - 1) / n_cta;
+                wpc = (wpc + kTileWords - 1) / kTileWords * kTileWords;
+                P.words_per_cta = wpc;
+                {
+                    Timed t(ctx, T_FEAT_SCATTER, 2);
+                    bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
+                    bucket_scatter_feat_kernel<<<(int)((w1 - w0 + wpc - 1) / wpc), 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
+                }
+                Timed t(ctx, T_FEAT, 1);
+                bucket_apply_feat_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, geo, ctx->d_bucket, P);
+            }
+            CKF(cudaGetLastError());
+            cleanup();
+            *out = f;
+            return PG_OK;
+        }
         const size_t smem = (size_t)kSlots * (P.vs + P.td) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
         int occ = 1;
         if (ctx->mode == kDense) CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, featurize_kernel<kDense>, kFeatThreads, smem));
@@ -703,18 +796,23 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     return PG_OK;
 }
 
-static void features_release(pg_features* f)
+// With a live ctx the buffers go back to the pool in stream order (no device-wide sync, and
+// the next step's allocations reuse them); the DLPack deleter has no ctx and frees synchronously.
+static void features_release(pg_features* f, pg_ctx* ctx = nullptr)
 {
     if (--f->refs > 0) return;
     cudaSetDevice(f->device);
-    cudaFree(f->abd_raw); cudaFree(f->tnf_raw); cudaFree(f->abd); cudaFree(f->tnf); cudaFree(f->weights); cudaFree(f->group_of_row);
+    void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
+    for (void* p : bufs) {
+        if (!p) continue;
+        if (ctx) cudaFreeAsync(p, ctx->stream); else cudaFree(p);
+    }
     delete f;
 }
 
 extern "C" void pg_features_free(pg_ctx* ctx, pg_features* f)
 {
-    (void)ctx;
-    if (f) features_release(f);
+    if (f) features_release(f, ctx);
 }
 
 extern "C" int64_t pg_features_rows(const pg_features* f) { return f ? f->rows : -1; }

@@ -9,16 +9,21 @@
 //             radix-partition the indices by slice.  A CTA bins one tile (256 words =
 //             8192 windows) in shared memory and appends one contiguous run per slice to
 //             that slice's region in HBM (coalesced; one cursor atomic per slice per tile).
-//   apply   : sweep the partitioned entries slice by slice; all SMs work on the same
-//             64 MiB slice at a time, so the counter updates / look-ups are L2 hits.
-// Region sizes come from a histogram pre-pass (ALU only, re-reads 0.375 B/base).
-// The stream is processed in segments so the entry buffer stays bounded.
+//   apply   : sweep the partitioned entries slice by slice.  Chunks are handed out IN
+//             ORDER from an atomic ticket, so everything in flight on the 148 SMs lies
+//             inside one 64 MiB slice (a static grid-stride loop lets CTAs drift apart
+//             until several slices are live and L2 thrashes - measured: 30 G RED/s).
+// Regions have a fixed capacity (kRegionSlack x the mean): the counter index is scrambled
+// by a bijection (kmer.cuh) so slices fill evenly for any base composition.  A run that
+// does not fit (pathological repeats) is applied straight to the table by the scatter
+// kernel instead - slower, never wrong.  The stream is processed in segments so the
+// entry buffer stays bounded.
 //
-// count   entries: u32 = index-in-slice | (run-1) << kSliceBits   (run merging of identical
-//                  consecutive windows, see count.cuh)
+// count   entries: u32 = index-in-slice | (run-1) << kSliceBits  (run merging of identical
+//                  adjacent windows: a poly-G tail is one entry, not 100 serialised REDs)
 // feature entries: u64 = index-in-slice | row << 32; the apply pass gathers the count,
-//                  bins it (count_kmer.cpp:90-93) and reduces (row, bin) tallies with
-//                  warp-aggregated RED into the abundance matrix.
+//                  bins it (count_kmer.cpp:90-93) and reduces equal (row, bin) pairs inside
+//                  the warp before one RED into the abundance matrix.
 #pragma once
 #include "featurize.cuh"
 #include "table.cuh"
@@ -29,202 +34,231 @@ constexpr int kSliceBits = 24;           // 2^24 u32 counters = 64 MiB per slice
 constexpr int kMaxBuckets = 64;
 constexpr int kTileWords = 256;          // one word per thread
 constexpr int kTileEntries = kTileWords * 32;
+constexpr int kChunk = 2048;             // entries per apply ticket (8 per thread)
+constexpr unsigned long long kOverflowRun = ~0ull;
 
 struct BucketGeom {
     int n_buckets;
-    uint32_t low_mask; // (1 << kSliceBits) - 1
+    uint32_t low_mask;                   // (1 << kSliceBits) - 1
+    unsigned long long cap;              // entries per region (multiple of 32)
 };
 
-// ---------------------------------------------------------------------------
-// windows of one word -> dense indices (registers), shared by hist and scatter
-// ---------------------------------------------------------------------------
-// COUNT flavour: merges runs of identical consecutive indices; ent[n] = idx, run[n] = length
-template <bool MERGE>
-__device__ __forceinline__ int word_indices(uint64_t lo, uint64_t hi, uint32_t mlo, uint32_t mhi, int k, uint32_t km,
-                                            uint32_t (&ent)[32], uint8_t (&run)[32])
+// device scratch, one per ctx
+struct BucketState {
+    unsigned long long cursors[kMaxBuckets]; // entries claimed per region (may exceed cap)
+    unsigned long long limits[kMaxBuckets];  // first offset that did not fit (cap if none)
+    unsigned long long ticket;
+};
+
+__global__ void bucket_reset_kernel(BucketState* st, unsigned long long cap)
 {
-    int n = 0;
+    if (threadIdx.x < kMaxBuckets) { st->cursors[threadIdx.x] = 0ull; st->limits[threadIdx.x] = cap; }
+    if (threadIdx.x == 0) st->ticket = 0ull;
+}
+
+// ---------------------------------------------------------------------------
+// windows of one word -> dense indices in registers (static indexing only)
+//   ent[i]  index of the window starting at base i (meaningful when bit i of valid)
+//   start   windows that open an entry
+//   cont    (MERGE only) windows identical to the window one base earlier: folded into
+//           that entry's run length
+// ---------------------------------------------------------------------------
+template <bool MERGE>
+__device__ __forceinline__ void word_windows(uint64_t lo, uint64_t hi, uint32_t mlo, uint32_t mhi, int k, uint32_t km,
+                                             uint32_t (&ent)[32], uint32_t& start, uint32_t& cont)
+{
     const uint64_t wmask = low_mask64(2 * k);
+    uint32_t valid = 0u;
+    cont = 0u;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const uint32_t mw = __funnelshift_r(mlo, mhi, i);
-        if ((mw & km) != km) continue;
+        const bool ok = (mw & km) == km;
         const uint32_t w = (uint32_t)((i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & wmask);
-        const uint32_t idx = dense_index_of_window(w, k);
-        if (MERGE && n > 0 && ent[n - 1] == idx) { ++run[n - 1]; continue; }
-        ent[n] = idx;
-        run[n] = 1;
-        ++n;
+        ent[i] = dense_index_of_window(w, k);
+        if (ok) valid |= 1u << i;
+        if (MERGE && i > 0 && ok && ((valid >> (i - 1)) & 1u) && ent[i] == ent[i - 1]) cont |= 1u << i;
     }
-    return n;
+    start = valid & ~cont;
 }
 
-// ---------------------------------------------------------------------------
-// pre-pass: entries per slice (must mirror the scatter kernels' emission exactly or be
-// an upper bound of it)
-// ---------------------------------------------------------------------------
-template <bool MERGE>
-__global__ void __launch_bounds__(256)
-bucket_hist_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ mask, int64_t w0, int64_t w1, int k,
-                   unsigned long long* __restrict__ totals, int n_buckets)
+// run length of the entry opened at base i: 1 + the continuation bits that follow it
+__device__ __forceinline__ uint32_t run_length(uint32_t cont, int i)
 {
-    __shared__ uint32_t h[kMaxBuckets];
-    if (threadIdx.x < kMaxBuckets) h[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t km = (1u << k) - 1u;
-    const uint64_t wmask = low_mask64(2 * k);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = w0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += stride) {
-        const uint32_t mlo = __ldg(mask + j);
-        if (mlo == 0u) continue;
-        const uint32_t mhi = __ldg(mask + j + 1);
-        const uint64_t lo = __ldg(codes + j), hi = __ldg(codes + j + 1);
-        uint32_t prev = 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const uint32_t mw = __funnelshift_r(mlo, mhi, i);
-            if ((mw & km) != km) continue;
-            const uint32_t w = (uint32_t)((i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & wmask);
-            const uint32_t idx = dense_index_of_window(w, k);
-            if (MERGE && idx == prev) continue;
-            prev = idx;
-            atomicAdd(&h[idx >> kSliceBits], 1u);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < n_buckets && h[threadIdx.x]) atomicAdd(totals + threadIdx.x, (unsigned long long)h[threadIdx.x]);
-}
-
-// totals -> region bases (exclusive scan, padded to 32 entries so runs start sector-aligned);
-// cursors reset; bases[n_buckets] = total capacity
-__global__ void bucket_scan_kernel(const unsigned long long* __restrict__ totals, unsigned long long* __restrict__ bases,
-                                   unsigned long long* __restrict__ cursors, int n_buckets)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long acc = 0;
-        for (int b = 0; b < n_buckets; ++b) {
-            bases[b] = acc;
-            cursors[b] = 0;
-            acc += (totals[b] + 31ull) & ~31ull;
-        }
-        bases[n_buckets] = acc;
-    }
+    const uint32_t following = i < 31 ? (cont >> (i + 1)) : 0u;
+    return (uint32_t)__ffs(~following); // 1 + number of trailing ones
 }
 
 // ---------------------------------------------------------------------------
 // tile-level radix partition in shared memory, then one run per slice to HBM
 // ---------------------------------------------------------------------------
 struct ScatterSmem {
-    uint32_t cnt[kMaxBuckets];      // entries of this tile per slice
-    uint32_t base[kMaxBuckets + 1]; // exclusive scan of cnt
-    unsigned long long gbase[kMaxBuckets]; // where this tile's run starts in the slice's region
+    uint32_t cnt[kMaxBuckets];             // entries of this tile per slice
+    uint32_t fill[kMaxBuckets];            // second cursor: position inside the tile's run
+    uint32_t base[kMaxBuckets];            // exclusive scan of cnt
+    unsigned long long gbase[kMaxBuckets]; // where this tile's run starts in the entry buffer
 };
 
-// after every thread has done  pos = atomicAdd(&S.cnt[b], 1)  for its entries and a
-// __syncthreads(): scan the counts and claim the global runs.  Ends with __syncthreads().
-__device__ __forceinline__ void scatter_claim(ScatterSmem& S, int n_buckets, const unsigned long long* __restrict__ bases,
-                                              unsigned long long* __restrict__ cursors)
+// after every thread has added its entries to S.cnt and a __syncthreads(): scan the counts
+// and claim the global runs.  Ends with __syncthreads().
+__device__ __forceinline__ void scatter_claim(ScatterSmem& S, const BucketGeom& geo, BucketState* st)
 {
-    if (threadIdx.x < 32) {
-        // n_buckets <= 64: two elements per lane
-        const int b0 = threadIdx.x * 2, b1 = b0 + 1;
-        const uint32_t c0 = b0 < n_buckets ? S.cnt[b0] : 0u, c1 = b1 < n_buckets ? S.cnt[b1] : 0u;
-        uint32_t inc = c0 + c1;
+    if (threadIdx.x < 32) { // n_buckets <= 64: lane owns slices `lane` and `lane + 32` (staging order is free)
+        const int b0 = threadIdx.x, b1 = b0 + 32;
+        const uint32_t c0 = b0 < geo.n_buckets ? S.cnt[b0] : 0u, c1 = b1 < geo.n_buckets ? S.cnt[b1] : 0u;
+        // both cursor atomics are issued before either result is used: one round trip, not two
+        const unsigned long long off0 = c0 ? atomicAdd(&st->cursors[b0], (unsigned long long)c0) : 0ull;
+        const unsigned long long off1 = c1 ? atomicAdd(&st->cursors[b1], (unsigned long long)c1) : 0ull;
+        uint32_t i0 = c0, i1 = c1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if ((int)threadIdx.x >= d) inc += t;
+            const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
+            if ((int)threadIdx.x >= d) { i0 += t0; i1 += t1; }
         }
-        const uint32_t ex = inc - (c0 + c1);
-        S.base[b0] = ex;
-        S.base[b1] = ex + c0;
-        if (threadIdx.x == 31) S.base[kMaxBuckets] = inc;
-        if (c0) S.gbase[b0] = bases[b0] + atomicAdd(cursors + b0, (unsigned long long)c0);
-        if (c1) S.gbase[b1] = bases[b1] + atomicAdd(cursors + b1, (unsigned long long)c1);
+        const uint32_t total0 = __shfl_sync(0xffffffffu, i0, 31);
+        S.base[b0] = i0 - c0;
+        S.base[b1] = total0 + i1 - c1;
+        if (c0) {
+            if (off0 + c0 > geo.cap) { atomicMin(&st->limits[b0], off0); S.gbase[b0] = kOverflowRun; }
+            else S.gbase[b0] = (unsigned long long)b0 * geo.cap + off0;
+        }
+        if (c1) {
+            if (off1 + c1 > geo.cap) { atomicMin(&st->limits[b1], off1); S.gbase[b1] = kOverflowRun; }
+            else S.gbase[b1] = (unsigned long long)b1 * geo.cap + off1;
+        }
     }
     __syncthreads();
 }
 
-// slice that staged entry e belongs to (binary search over <= 64 prefix sums)
-__device__ __forceinline__ int bucket_of_staged(const ScatterSmem& S, uint32_t e)
-{
-    int lo = 0, hi = kMaxBuckets; // base[lo] <= e < base[hi]
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-        const int mid = (lo + hi) >> 1;
-        if (S.base[mid] <= e) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // ---- count ----------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bucket_scatter_count_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ maskC, int64_t w0, int64_t w1, int k,
-                            BucketGeom geo, const unsigned long long* __restrict__ bases, unsigned long long* __restrict__ cursors,
-                            uint32_t* __restrict__ entries)
+                            BucketGeom geo, BucketState* __restrict__ st, uint32_t* __restrict__ entries, uint32_t* __restrict__ table)
 {
     __shared__ ScatterSmem S;
     __shared__ uint32_t stage[kTileEntries];
     const uint32_t km = (1u << k) - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (threadIdx.x < kMaxBuckets) S.cnt[threadIdx.x] = 0u;
+        if (threadIdx.x < kMaxBuckets) { S.cnt[threadIdx.x] = 0u; S.fill[threadIdx.x] = 0u; }
         __syncthreads();
         const int64_t j = w0 + t * kTileWords + threadIdx.x;
-        uint32_t ent[32];
-        uint8_t run[32];
-        uint16_t pos[32];
-        int n = 0;
+        uint32_t ent[32], start = 0u, cont = 0u;
         if (j < w1) {
             const uint32_t mlo = __ldg(maskC + j);
-            if (mlo != 0u) n = word_indices<true>(__ldg(codes + j), __ldg(codes + j + 1), mlo, __ldg(maskC + j + 1), k, km, ent, run);
+            if (mlo != 0u) word_windows<true>(__ldg(codes + j), __ldg(codes + j + 1), mlo, __ldg(maskC + j + 1), k, km, ent, start, cont);
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < n) pos[i] = (uint16_t)atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
+            if ((start >> i) & 1u) atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
         __syncthreads();
-        scatter_claim(S, geo.n_buckets, bases, cursors);
+        scatter_claim(S, geo, st);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < n) stage[S.base[ent[i] >> kSliceBits] + pos[i]] = (ent[i] & geo.low_mask) | ((uint32_t)(run[i] - 1) << kSliceBits);
+            if ((start >> i) & 1u) {
+                const uint32_t b = ent[i] >> kSliceBits;
+                const uint32_t at = S.base[b] + atomicAdd(&S.fill[b], 1u);
+                stage[at] = (ent[i] & geo.low_mask) | ((run_length(cont, i) - 1u) << kSliceBits);
+            }
         __syncthreads();
-        const uint32_t total = S.base[kMaxBuckets];
-        for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-            const int b = bucket_of_staged(S, e);
-            __stcs(entries + S.gbase[b] + (e - S.base[b]), stage[e]);
+        for (int b = warp; b < geo.n_buckets; b += 8) { // one warp copies one slice's run: coalesced, no search
+            const uint32_t n = S.cnt[b];
+            if (!n) continue;
+            const uint32_t* src = stage + S.base[b];
+            if (S.gbase[b] != kOverflowRun) {
+                uint32_t* dst = entries + S.gbase[b];
+                for (uint32_t e = lane; e < n; e += 32) __stcs(dst + e, src[e]);
+            } else { // region full: apply the run here
+                for (uint32_t e = lane; e < n; e += 32)
+                    atomicAdd(table + (((uint32_t)b << kSliceBits) | (src[e] & geo.low_mask)), (src[e] >> kSliceBits) + 1u);
+            }
         }
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256)
-bucket_apply_count_kernel(const uint32_t* __restrict__ entries, const unsigned long long* __restrict__ bases,
-                          const unsigned long long* __restrict__ cursors, BucketGeom geo, uint32_t* __restrict__ table)
+// ordered tickets over the filled part of every region: ticket -> (slice, offset)
+struct ApplySmem {
+    unsigned long long fill[kMaxBuckets];           // valid entries per region
+    unsigned long long chunk_base[kMaxBuckets + 1]; // prefix sum of chunks per region
+    unsigned long long ticket;
+};
+
+__device__ __forceinline__ void apply_prologue(ApplySmem& A, const BucketGeom& geo, const BucketState* st)
 {
-    __shared__ unsigned long long sb[kMaxBuckets + 1], sf[kMaxBuckets];
-    if (threadIdx.x <= geo.n_buckets) sb[threadIdx.x] = bases[threadIdx.x];
-    if (threadIdx.x < geo.n_buckets) sf[threadIdx.x] = cursors[threadIdx.x];
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int b = 0; b < geo.n_buckets; ++b) {
+            const unsigned long long f = min(min(st->cursors[b], st->limits[b]), geo.cap);
+            A.fill[b] = f;
+            A.chunk_base[b] = acc;
+            acc += (f + kChunk - 1) / kChunk;
+        }
+        A.chunk_base[geo.n_buckets] = acc;
+    }
     __syncthreads();
-    const unsigned long long cap = sb[geo.n_buckets];
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+}
+
+__global__ void __launch_bounds__(256)
+bucket_apply_count_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, BucketState* __restrict__ st, uint32_t* __restrict__ table)
+{
+    __shared__ ApplySmem A;
+    apply_prologue(A, geo, st);
+    const unsigned long long n_chunks = A.chunk_base[geo.n_buckets];
     int b = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
-        while (b + 1 < geo.n_buckets && sb[b + 1] <= i) ++b; // i only grows
-        if (i - sb[b] >= sf[b]) continue;                     // padding between regions
-        const uint32_t e = __ldcs(entries + i);
-        atomicAdd(table + (((uint32_t)b << kSliceBits) | (e & geo.low_mask)), (e >> kSliceBits) + 1u);
+    for (;;) {
+        if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
+        __syncthreads();
+        const unsigned long long c = A.ticket;
+        __syncthreads();
+        if (c >= n_chunks) break;
+        while (A.chunk_base[b + 1] <= c) ++b; // tickets only grow
+        const unsigned long long off = (c - A.chunk_base[b]) * kChunk;
+        const uint32_t n = (uint32_t)min((unsigned long long)kChunk, A.fill[b] - off);
+        const uint32_t* src = entries + (unsigned long long)b * geo.cap + off;
+        uint32_t* slice = table + ((size_t)b << kSliceBits);
+        uint32_t e[kChunk / 256];
+#pragma unroll
+        for (int u = 0; u < kChunk / 256; ++u) {
+            const uint32_t i = threadIdx.x + 256u * u;
+            e[u] = i < n ? __ldcs(src + i) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < kChunk / 256; ++u)
+            if (threadIdx.x + 256u * u < n) atomicAdd(slice + (e[u] & geo.low_mask), (e[u] >> kSliceBits) + 1u);
     }
 }
 
 // ---- featurize --------------------------------------------------------------
+// one (row, bin) tally per live lane; lanes with equal keys elect a leader -> one RED
+__device__ __forceinline__ void abd_reduce_warp(const FeatParams& P, bool live, unsigned long long key)
+{
+    const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const uint32_t peers = __match_any_sync(live_mask, key);
+        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
+            atomicAdd(P.abd + (int64_t)(key >> 32) * P.vs + (uint32_t)key, (uint32_t)__popc(peers));
+    }
+}
+
+// count -> (row, bin) key, false when the k-mer is absent or beyond the histogram
+__device__ __forceinline__ bool abd_key(const FeatParams& P, uint32_t c, uint32_t row, unsigned long long& key)
+{
+    if (c == 0u) return false; // absent k-mers are skipped (count_kmer.cpp:87)
+    c &= kCountMask;
+    if (c >= P.clamp) return false;
+    key = ((unsigned long long)row << 32) | abd_bin(P, c);
+    return true;
+}
+
 // Same tile walk as featurize_kernel (featurize.cuh): TNF goes to block-private bins, but
 // the 15-mer windows are not looked up here - their (index, row) pairs are partitioned by
-// slice for bucket_apply_feat_kernel.  Words that straddle a cloud boundary, and clouds
-// beyond the TNF slots, take the direct path of featurize.cuh (rare).
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(256)
-bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, BucketGeom geo,
-                           const unsigned long long* __restrict__ bases, unsigned long long* __restrict__ cursors,
+// slice for bucket_apply_feat_kernel.  Words that straddle a cloud boundary take the
+// direct path of featurize.cuh (rare: one word per cloud).  P.maskF is the cleaned
+// feature mask: dropped clouds and PG_READ_NOFEAT reads are already zero in it.
+__global__ void __launch_bounds__(256, 2)
+bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, BucketGeom geo, BucketState* __restrict__ st,
                            unsigned long long* __restrict__ entries)
 {
     extern __shared__ uint32_t smem[];
@@ -245,26 +279,31 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
     const int k = P.table.k;
     const uint32_t km = (1u << k) - 1u, tm = (1u << P.tnf_k) - 1u;
     const uint32_t tmask = (1u << (2 * P.tnf_k)) - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     int64_t g_cur = advance_group(P.gstart, P.n_groups, 0, w_begin * 32);
-    for (int64_t tile = w_begin; tile < w_end; tile += kTileWords) {
+    int64_t tile = w_begin;
+    while (tile < w_end) {
         const int64_t tile_end = min(tile + (int64_t)kTileWords, w_end);
         const int64_t p0 = tile * 32, p1 = min(tile_end * 32, P.n_bytes);
         const int64_t g_lo = advance_group(P.gstart, P.n_groups, g_cur, p0);
         const int64_t g_hi = advance_group(P.gstart, P.n_groups, g_lo, p1 - 1);
         g_cur = g_lo;
         const bool single = (g_hi == g_lo);
-        if (threadIdx.x < kMaxBuckets) S.cnt[threadIdx.x] = 0u;
+        if (single && __ldg(P.row_of_group + g_lo) < 0) { // dropped cloud: jump to the tile holding its end
+            const int64_t nxt = __ldg(P.gstart + g_lo + 1) >> 5;
+            const int64_t jump = w_begin + ((nxt - w_begin) / kTileWords) * kTileWords;
+            tile = max(tile + (int64_t)kTileWords, jump);
+            continue;
+        }
+        if (threadIdx.x < kMaxBuckets) { S.cnt[threadIdx.x] = 0u; S.fill[threadIdx.x] = 0u; }
         __syncthreads();
 
         const int64_t j = tile + threadIdx.x;
-        uint32_t ent[32];
-        uint8_t run[32];
-        uint16_t pos[32];
-        int n = 0;
+        uint32_t ent[32], start = 0u, cont = 0u;
         int32_t row = -1;
         uint32_t mlo = 0u;
-        if (j < tile_end) mlo = __ldg(P.maskF + j); // maskF here = maskR: dropped clouds and NOFEAT reads already cleared
+        if (j < tile_end) mlo = __ldg(P.maskF + j);
         if (mlo != 0u) {
             const uint32_t mhi = __ldg(P.maskF + j + 1);
             const uint64_t lo = __ldg(P.codes + j), hi = __ldg(P.codes + j + 1);
@@ -284,10 +323,10 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
                             atomicAdd(tnf_row + lut_s[w4], 1u);
                         }
                     }
-                    n = word_indices<false>(lo, hi, mlo, mhi, k, km, ent, run);
+                    word_windows<false>(lo, hi, mlo, mhi, k, km, ent, start, cont);
                 }
             } else {
-                // a cloud boundary inside the word: direct look-ups (featurize.cuh slow path)
+                // a cloud boundary inside the word: direct look-ups, abundance straight to the global row
                 int64_t next_start = __ldg(P.gstart + g + 1);
                 int32_t r = __ldg(P.row_of_group + g);
                 for (int i = 0; i < 32; ++i) {
@@ -300,38 +339,49 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
                     if (r < 0 || !((mlo >> i) & 1u)) continue;
                     const int64_t slot = g - g_lo;
                     uint32_t* tnf_row = slot < kSlots ? bins + slot * P.td : P.tnf + (int64_t)r * P.td;
-                    // abundance goes straight to the global row (no abundance slots in this kernel)
-                    FeatParams Q = P;
-                    feat_one<kDense>(Q, lo, hi, mlo, mhi, i, P.abd + (int64_t)r * P.vs, tnf_row, lut_s);
+                    feat_one<kDense>(P, lo, hi, mlo, mhi, i, P.abd + (int64_t)r * P.vs, tnf_row, lut_s);
                 }
             }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < n) pos[i] = (uint16_t)atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
+            if ((start >> i) & 1u) atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
         __syncthreads();
-        scatter_claim(S, geo.n_buckets, bases, cursors);
+        scatter_claim(S, geo, st);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < n) {
-                const uint32_t at = S.base[ent[i] >> kSliceBits] + pos[i];
+            if ((start >> i) & 1u) {
+                const uint32_t b = ent[i] >> kSliceBits;
+                const uint32_t at = S.base[b] + atomicAdd(&S.fill[b], 1u);
                 stage_idx[at] = ent[i] & geo.low_mask;
                 stage_row[at] = (uint32_t)row;
             }
         __syncthreads();
-        const uint32_t total = S.base[kMaxBuckets];
-        for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-            const int b = bucket_of_staged(S, e);
-            __stcs(entries + S.gbase[b] + (e - S.base[b]), (unsigned long long)stage_idx[e] | ((unsigned long long)stage_row[e] << 32));
+        for (int b = warp; b < geo.n_buckets; b += 8) {
+            const uint32_t n = S.cnt[b];
+            if (!n) continue;
+            const uint32_t *si = stage_idx + S.base[b], *sr = stage_row + S.base[b];
+            if (S.gbase[b] != kOverflowRun) {
+                unsigned long long* dst = entries + S.gbase[b];
+                for (uint32_t e = lane; e < n; e += 32) __stcs(dst + e, (unsigned long long)si[e] | ((unsigned long long)sr[e] << 32));
+            } else { // region full: look the run up here (whole warp stays in the loop for the reduction)
+                for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    unsigned long long key = 0;
+                    bool live = false;
+                    if (e < n) live = abd_key(P, __ldg(P.table.counts + (((uint32_t)b << kSliceBits) | si[e])), sr[e], key);
+                    abd_reduce_warp(P, live, key);
+                }
+            }
         }
         // TNF bins: same carry rule as featurize_kernel
         const bool carry = single && tile_end < w_end && (g_lo + 1 >= P.n_groups || __ldg(P.gstart + g_lo + 1) > p1);
         if (!carry) {
             const int64_t ns = min((int64_t)kSlots, g_hi - g_lo + 1);
-            for (int64_t s = 0; s < ns; ++s) {
-                const int32_t r = __ldg(P.row_of_group + g_lo + s);
+            for (int64_t s2 = 0; s2 < ns; ++s2) {
+                const int32_t r = __ldg(P.row_of_group + g_lo + s2);
                 if (r < 0) continue;
-                uint32_t* src = bins + s * P.td;
+                uint32_t* src = bins + s2 * P.td;
                 uint32_t* dst = P.tnf + (int64_t)r * P.td;
                 for (int b = threadIdx.x; b < P.td; b += blockDim.x) {
                     const uint32_t v = src[b];
@@ -340,57 +390,63 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
             }
         }
         __syncthreads();
+        tile = tile_end;
     }
 }
 
-// sweep the partitioned (index, row) pairs slice by slice: gather (L2 hit), bin, and
-// reduce equal (row, bin) pairs inside the warp before the RED
+// sweep the partitioned (index, row) pairs slice by slice: gather (L2 hit), bin, reduce
 __global__ void __launch_bounds__(256)
-bucket_apply_feat_kernel(const unsigned long long* __restrict__ entries, const unsigned long long* __restrict__ bases,
-                         const unsigned long long* __restrict__ cursors, BucketGeom geo, const FeatParams P)
+bucket_apply_feat_kernel(const unsigned long long* __restrict__ entries, BucketGeom geo, BucketState* __restrict__ st, const FeatParams P)
 {
-    __shared__ unsigned long long sb[kMaxBuckets + 1], sf[kMaxBuckets];
-    if (threadIdx.x <= geo.n_buckets) sb[threadIdx.x] = bases[threadIdx.x];
-    if (threadIdx.x < geo.n_buckets) sf[threadIdx.x] = cursors[threadIdx.x];
-    __syncthreads();
-    const unsigned long long cap = sb[geo.n_buckets];
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long cap32 = (cap + 31ull) & ~31ull; // whole warps stay in the loop for the match
+    __shared__ ApplySmem A;
+    apply_prologue(A, geo, st);
+    const unsigned long long n_chunks = A.chunk_base[geo.n_buckets];
     int b = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap32; i += stride) {
-        while (b + 1 < geo.n_buckets && sb[b + 1] <= i) ++b;
-        uint32_t key = 0xFFFFFFFFu; // (row * vs + bin) would overflow 32 bits for big matrices: keep row and bin apart
-        uint32_t row = 0, bin = 0;
-        bool live = false;
-        if (i < cap && i - sb[b] < sf[b]) {
-            const unsigned long long e = __ldcs(entries + i);
-            uint32_t c = __ldg(P.table.counts + (((uint32_t)b << kSliceBits) | ((uint32_t)e & geo.low_mask)));
-            if (c != 0u) {
-                c &= kCountMask;
-                if (c < P.clamp) {
-                    bin = abd_bin(P, c);
-                    row = (uint32_t)(e >> 32);
-                    live = true;
-                    key = (row << 10) ^ bin; // match hint only; equality is re-checked below
-                }
-            }
+    for (;;) {
+        if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
+        __syncthreads();
+        const unsigned long long c = A.ticket;
+        __syncthreads();
+        if (c >= n_chunks) break;
+        while (A.chunk_base[b + 1] <= c) ++b;
+        const unsigned long long off = (c - A.chunk_base[b]) * kChunk;
+        const uint32_t n = (uint32_t)min((unsigned long long)kChunk, A.fill[b] - off);
+        const unsigned long long* src = entries + (unsigned long long)b * geo.cap + off;
+        const uint32_t* slice = P.table.counts + ((size_t)b << kSliceBits);
+        unsigned long long e[kChunk / 256];
+        uint32_t cnt[kChunk / 256];
+#pragma unroll
+        for (int u = 0; u < kChunk / 256; ++u) {
+            const uint32_t i = threadIdx.x + 256u * u;
+            e[u] = i < n ? __ldcs(src + i) : 0ull;
         }
-        // warp aggregation: lanes with the same (row, bin) elect one leader
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        if (live) {
-            // the hint can collide: count only true equals among the peers
-            uint32_t n_eq = 0, first = 32;
-            uint32_t m = peers;
-            while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t r2 = __shfl_sync(peers, row, l), b2 = __shfl_sync(peers, bin, l);
-                if (r2 == row && b2 == bin) { ++n_eq; if (first == 32) first = l; }
-            }
-            if (first == (threadIdx.x & 31)) atomicAdd(P.abd + (int64_t)row * P.vs + bin, n_eq);
-        } else if (peers) {
-            // dead lanes matched each other on the sentinel; they still have to take part in the shuffles above? no:
-            // shuffles are issued with mask = peers, and dead lanes' peers contain only dead lanes.
+#pragma unroll
+        for (int u = 0; u < kChunk / 256; ++u)
+            cnt[u] = (threadIdx.x + 256u * u < n) ? __ldg(slice + ((uint32_t)e[u] & geo.low_mask)) : 0u;
+#pragma unroll
+        for (int u = 0; u < kChunk / 256; ++u) {
+            unsigned long long key = 0;
+            const bool live = abd_key(P, cnt[u], (uint32_t)(e[u] >> 32), key);
+            abd_reduce_warp(P, live, key);
+        }
+    }
+}
+
+// featurize works on a copy of maskF from which dropped clouds are removed, so the scatter
+// kernel needs no per-word cloud look-up for them
+__global__ void __launch_bounds__(256)
+clear_dropped_groups_kernel(const int64_t* __restrict__ gstart, const int32_t* __restrict__ row_of_group, int64_t n_groups,
+                            uint32_t* __restrict__ maskR)
+{
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (__ldg(row_of_group + g) >= 0) continue;
+        const int64_t lo = gstart[g], hi = gstart[g + 1];
+        if (lo >= hi) continue;
+        const int64_t wlo = lo >> 5, whi = (hi - 1) >> 5;
+        for (int64_t w = wlo + threadIdx.x; w <= whi; w += blockDim.x) {
+            const int64_t a = max(lo, w << 5), b = min(hi, (w + 1) << 5);
+            const uint32_t bits = (uint32_t)(((1ull << (b - a)) - 1ull) << (a - (w << 5)));
+            if (bits == 0xFFFFFFFFu) maskR[w] = 0u; else atomicAnd(&maskR[w], ~bits);
         }
     }
 }

@@ -65,43 +65,86 @@ PG_HD uint64_t canonical_of_fwd(uint64_t v, int k)
 
 // ---------------------------------------------------------------------------
 // Dense (direct-addressed) counter index for k <= 16.
-//   even k : index = reference canonical key, 4^k counters.
+//   even k : class id = reference canonical key, 4^k counters.
 //   odd  k : v and rc(v) have complementary middle bases (codes c and c^2), so
 //            exactly one of them has bit k clear; take that one and squeeze the
 //            bit out: a bijection {v, rc(v)} -> [0, 4^k / 2).  Halves the table
 //            (k = 15: 2^29 counters = 2 GiB) and needs no min().
+// The class id is then SCRAMBLED by an invertible mixing function on its bit width
+// (multiply by an odd constant, xor-shift by half the width, multiply again).  The
+// table is swept in contiguous slices (bucket.cuh); scrambling makes every slice
+// receive the same share of the k-mers whatever the base composition of the
+// genomes (an AT-rich community would otherwise fill some slices 2-4x more than
+// others).  It is a bijection, so counts are unchanged; export inverts it.
 // ---------------------------------------------------------------------------
 PG_HD uint64_t dense_entries(int k) { return (k & 1) ? (1ull << (2 * k - 1)) : (1ull << (2 * k)); }
+PG_HD int dense_bits(int k) { return (k & 1) ? 2 * k - 1 : 2 * k; }
+
+constexpr uint32_t kMixA = 0x9E3779B1u, kMixB = 0x85EBCA6Bu;
+constexpr uint32_t mod_inverse32(uint32_t a)
+{
+    uint32_t x = a; // Newton: doubles the number of correct low bits each round (a*a = 1 mod 8)
+    for (int i = 0; i < 5; ++i) x *= 2u - a * x;
+    return x;
+}
+constexpr uint32_t kMixAInv = mod_inverse32(kMixA), kMixBInv = mod_inverse32(kMixB);
+static_assert(kMixA * kMixAInv == 1u && kMixB * kMixBInv == 1u, "modular inverses");
+
+PG_HD uint32_t scramble_bits(uint32_t x, int bits)
+{
+    if (bits < 8) return x;
+    const uint32_t m = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    const int h = (bits + 1) >> 1;
+    x = (x * kMixA) & m;
+    x ^= x >> h;
+    return (x * kMixB) & m;
+}
+PG_HD uint32_t unscramble_bits(uint32_t y, int bits)
+{
+    if (bits < 8) return y;
+    const uint32_t m = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    const int h = (bits + 1) >> 1;
+    y = (y * kMixBInv) & m;
+    y ^= y >> h; // 2h >= bits: the xor-shift is its own inverse
+    return (y * kMixAInv) & m;
+}
 
 PG_HD uint32_t dense_index_of_window(uint32_t w, int k)
 {
     uint32_t f = fwd_of_window32(w, k);
     uint32_t r = w ^ (0xAAAAAAAAu & (uint32_t)low_mask64(2 * k));
+    uint32_t id;
     if (k & 1) {
         uint32_t x = ((f >> k) & 1u) ? r : f;
-        return ((x >> (k + 1)) << k) | (x & ((1u << k) - 1u));
+        id = ((x >> (k + 1)) << k) | (x & ((1u << k) - 1u));
+    } else {
+        id = f < r ? f : r;
     }
-    return f < r ? f : r;
+    return scramble_bits(id, dense_bits(k));
 }
 
 PG_HD uint64_t dense_index_of_fwd(uint64_t v, int k)
 {
     uint64_t r = (rev_groups64(v) >> (64 - 2 * k)) ^ (0xAAAAAAAAAAAAAAAAull & low_mask64(2 * k));
+    uint64_t id;
     if (k & 1) {
         uint64_t x = ((v >> k) & 1ull) ? r : v;
-        return ((x >> (k + 1)) << k) | (x & ((1ull << k) - 1ull));
+        id = ((x >> (k + 1)) << k) | (x & ((1ull << k) - 1ull));
+    } else {
+        id = v < r ? v : r;
     }
-    return v < r ? v : r;
+    return scramble_bits((uint32_t)id, dense_bits(k));
 }
 
 // dense index -> reference canonical key
 PG_HD uint64_t key_of_dense_index(uint64_t idx, int k)
 {
+    uint64_t id = unscramble_bits((uint32_t)idx, dense_bits(k));
     if (k & 1) {
-        uint64_t x = ((idx >> k) << (k + 1)) | (idx & ((1ull << k) - 1ull));
+        uint64_t x = ((id >> k) << (k + 1)) | (id & ((1ull << k) - 1ull));
         return canonical_of_fwd(x, k);
     }
-    return idx;
+    return id;
 }
 
 // 64-bit finaliser (splitmix64) - slot hash of the open-addressing table

@@ -135,6 +135,29 @@ def test_tiny_clouds_overflow_the_slots(tmp_path, oracle):
     assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
 
 
+@pytest.mark.parametrize("env", [{}, {"PG_SEG_WORDS": "512"}, {"PG_FORCE_DIRECT": "1"}, {"PG_REGION_SLACK": "0.3"},
+                                 {"PG_REGION_SLACK": "0.02", "PG_SEG_WORDS": "2048"}])
+def test_sliced_and_direct_table_paths_agree(tmp_path, oracle, monkeypatch, env):
+    """k = 15 uses the L2-sliced path (bucket.cuh) by default; PG_SEG_WORDS forces many
+    segments on a small input, PG_FORCE_DIRECT the one-kernel path, PG_REGION_SLACK < 1 makes
+    slice regions overflow so runs are applied by the scatter kernels.  All must equal the oracle."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    data = synth.generate(n_barcodes=150, mean_pairs=14, read_len=100, n_genomes=3, genome_len=60_000, frag_len=8_000,
+                          seed=77, unbarcoded_pairs=40, n_rate=0.003, lower_rate=0.002)
+    path = synth.write_interleaved(str(tmp_path / "i.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    fq = _lib.Fastq(path)
+    ctx = _ctx()
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    g_abd, g_tnf = feats.raw()
+    assert _names(fq, feats) == list(names)
+    assert np.array_equal(g_tnf, tnf) and np.array_equal(g_abd, abd)
+    keys, counts = ctx.table_export()
+    wk, wv = _oracle_table_arrays(oracle.count_fastq(path, 15))
+    assert np.array_equal(keys, wk) and np.array_equal(counts.astype(np.uint64), wv)
+
+
 def test_ragged_lengths_and_long_reads(tmp_path, oracle):
     rng = np.random.default_rng(8)
     recs = []
