@@ -258,7 +258,8 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     }
     CKC(cudaFuncSetAttribute(featurize_kernel<kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaFuncSetAttribute(featurize_kernel<kHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
 #undef CKC
     *out = ctx;
@@ -471,15 +472,16 @@ static int count_bucketed(pg_ctx* ctx, pg_batch* b)
     uint32_t* entries;
     CK(dmalloc(ctx, &entries, (size_t)geo.cap * geo.n_buckets));
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_count_kernel, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_count_kernel<15>, 256, 0));
     for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
         const int64_t w1 = std::min(b->n_words, w0 + seg_words);
         const int64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
         {
             Timed t(ctx, T_COUNT_SCATTER, 2);
             bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-            bucket_scatter_count_kernel<<<(int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ), 256, 0, ctx->stream>>>(
-                b->codes, b->maskC, w0, w1, ctx->p.k, geo, ctx->d_bucket, entries, ctx->counts);
+            const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ);
+            if (ctx->p.k == 15) bucket_scatter_count_kernel<15><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, w0, w1, 15, geo, ctx->d_bucket, entries, ctx->counts);
+            else bucket_scatter_count_kernel<0><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, w0, w1, ctx->p.k, geo, ctx->d_bucket, entries, ctx->counts);
         }
         Timed t(ctx, T_COUNT, 1);
         bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
@@ -752,9 +754,9 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
             const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
             const BucketGeom geo = bucket_geom(ctx, seg_words);
             CKF(dmalloc(ctx, &feat_entries, (size_t)geo.cap * geo.n_buckets));
-            const size_t smem_s = (size_t)2 * kTileEntries * sizeof(uint32_t) + (size_t)kSlots * P.td * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
+            const size_t smem_s = (size_t)2 * kTileEntries * sizeof(uint32_t) + ((size_t)kSlots * P.td + 2) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
             int occ_s = 1;
-            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, bucket_scatter_feat_kernel, 256, smem_s));
+            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, bucket_scatter_feat_kernel<15>, 256, smem_s));
             if (occ_s < 1) { cleanup(); pg_features_free(ctx, f); return fail(ctx, PG_ERR_INVALID, "tnf_k too large for shared memory"); }
             for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
                 const int64_t w1 = std::min(b->n_words, w0 + seg_words);
@@ -765,7 +767,9 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 {
                     Timed t(ctx, T_FEAT_SCATTER, 2);
                     bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-                    bucket_scatter_feat_kernel<<<(int)((w1 - w0 + wpc - 1) / wpc), 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
+                    const int grid = (int)((w1 - w0 + wpc - 1) / wpc);
+                    if (ctx->p.k == 15) bucket_scatter_feat_kernel<15><<<grid, 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
+                    else bucket_scatter_feat_kernel<0><<<grid, 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
                 }
                 Timed t(ctx, T_FEAT, 1);
                 bucket_apply_feat_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, geo, ctx->d_bucket, P);

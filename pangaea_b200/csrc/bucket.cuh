@@ -30,7 +30,7 @@
 
 namespace pg {
 
-constexpr int kSliceBits = 24;           // 2^24 u32 counters = 64 MiB per slice
+constexpr int kSliceBits = 23;           // 2^23 u32 counters = 32 MiB per slice (64 MiB slices get written back 4.5x: profiles/)
 constexpr int kMaxBuckets = 64;
 constexpr int kTileWords = 256;          // one word per thread
 constexpr int kTileEntries = kTileWords * 32;
@@ -57,29 +57,90 @@ __global__ void bucket_reset_kernel(BucketState* st, unsigned long long cap)
 }
 
 // ---------------------------------------------------------------------------
-// windows of one word -> dense indices in registers (static indexing only)
-//   ent[i]  index of the window starting at base i (meaningful when bit i of valid)
-//   start   windows that open an entry
-//   cont    (MERGE only) windows identical to the window one base earlier: folded into
-//           that entry's run length
+// Shared-memory atomics without divergence.  A conditional atomicAdd compiles to
+// BSSY / BRA / ATOMS / BSYNC (ptxas will not predicate ATOMS.POPC.INC); with 64 of them per
+// thread that is a third of the kernel.  Instead every lane always issues the atomic and
+// windows that emit nothing go to a dummy slot (index kMaxBuckets); same-address shared
+// atomics are aggregated by the hardware, so the dummy is not a hot spot
+// (profiles/microbench_r01.txt: 4 hot bins run faster than 136 uniform ones).
 // ---------------------------------------------------------------------------
-template <bool MERGE>
-__device__ __forceinline__ void word_windows(uint64_t lo, uint64_t hi, uint32_t mlo, uint32_t mhi, int k, uint32_t km,
-                                             uint32_t (&ent)[32], uint32_t& start, uint32_t& cont)
+__device__ __forceinline__ void smem_inc_if(uint32_t* cnt, uint32_t slot, uint32_t on)
 {
-    const uint64_t wmask = low_mask64(2 * k);
-    uint32_t valid = 0u;
-    cont = 0u;
+    atomicAdd(cnt + (on ? slot : (uint32_t)kMaxBuckets), 1u);
+}
+// if (on) stage[ fill[slot]++ ] = v      (fill already holds the run's base offset)
+__device__ __forceinline__ void smem_push_if(uint32_t* fill, uint32_t slot, uint32_t* stage, uint32_t v, uint32_t on)
+{
+    const uint32_t at = atomicAdd(fill + (on ? slot : (uint32_t)kMaxBuckets), 1u);
+    if (on) stage[at] = v;
+}
+// same, two payload words into two staging arrays (featurize: index, row)
+__device__ __forceinline__ void smem_push2_if(uint32_t* fill, uint32_t slot, uint32_t* stage_a, uint32_t* stage_b, uint32_t va, uint32_t vb, uint32_t on)
+{
+    const uint32_t at = atomicAdd(fill + (on ? slot : (uint32_t)kMaxBuckets), 1u);
+    if (on) { stage_a[at] = va; stage_b[at] = vb; }
+}
+
+// ---------------------------------------------------------------------------
+// bit i of the result: mask bits i .. i+k-1 are all set (the k-mer window starting at base
+// i of this word is valid), i in 0..31, k in 1..32.  Binary decomposition of k: ~4 AND/shift
+// pairs on the 64-bit mask for all 32 windows at once instead of a funnel shift + compare
+// per window.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t window_valid_mask(uint32_t mlo, uint32_t mhi, int k)
+{
+    uint64_t v = ((uint64_t)mhi << 32) | mlo; // v(i) = AND of mask[i .. i+len-1]
+    uint64_t acc = ~0ull;                     // acc(i) = AND of mask[i .. i+off-1]
+    int off = 0;
+#pragma unroll
+    for (int bit = 0, len = 1; bit < 6; ++bit, len <<= 1) {
+        if (k & len) { acc &= v >> off; off += len; }
+        v &= v >> len;
+    }
+    return (uint32_t)acc;
+}
+
+// ---------------------------------------------------------------------------
+// dense indices of the 32 windows of one word, in registers (static indexing only).
+// KT > 0 fixes k at compile time (15, the production value: shifts and masks become
+// immediates).  Rolling update instead of re-extracting every window: with w_i the
+// LSB-first window at base i (its reverse complement is w_i ^ 0xAAAA.., its forward value
+// the group-reversed w_i),
+//   rc_{i+1}  = (rc_i >> 2)  | ((c ^ 2) << 2(k-1))        c = code of base i + k
+//   fwd_{i+1} = ((fwd_i << 2) | c) & mask
+// min_diff == 0 iff two neighbouring windows have the same index (homopolymer runs).
+// ---------------------------------------------------------------------------
+template <int KT, bool MERGE>
+__device__ __forceinline__ void word_indices(uint64_t lo, uint64_t hi, int k_rt, uint32_t (&ent)[32], uint32_t& min_diff)
+{
+    const int k = KT ? KT : k_rt;
+    const uint32_t wmask = (uint32_t)low_mask64(2 * k);
+    const uint32_t w0 = (uint32_t)lo & wmask;
+    uint32_t f = fwd_of_window32(w0, k);
+    uint32_t r = w0 ^ (0xAAAAAAAAu & wmask);
+    const uint64_t tail = (lo >> (2 * k)) | (hi << (64 - 2 * k)); // codes of bases k .. k+31 (k in 1..16)
+    const int top = 2 * (k - 1);
+    min_diff = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const uint32_t mw = __funnelshift_r(mlo, mhi, i);
-        const bool ok = (mw & km) == km;
-        const uint32_t w = (uint32_t)((i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & wmask);
-        ent[i] = dense_index_of_window(w, k);
-        if (ok) valid |= 1u << i;
-        if (MERGE && i > 0 && ok && ((valid >> (i - 1)) & 1u) && ent[i] == ent[i - 1]) cont |= 1u << i;
+        ent[i] = dense_index_of_pair(f, r, k);
+        if (MERGE && i > 0) min_diff = min(min_diff, ent[i] ^ ent[i - 1]);
+        const uint32_t c = (uint32_t)(tail >> (2 * i)) & 3u;
+        f = ((f << 2) | c) & wmask;
+        r = (r >> 2) | ((c ^ 2u) << top);
     }
-    start = valid & ~cont;
+}
+
+// windows identical to the window one base earlier (both valid): folded into that entry's
+// run length, so a poly-G tail is one entry instead of 100 REDs serialised on one L2 address.
+// Only evaluated for the rare words where word_indices saw two equal neighbours.
+__device__ __forceinline__ uint32_t continuation_mask(const uint32_t (&ent)[32], uint32_t valid)
+{
+    uint32_t cont = 0u;
+#pragma unroll
+    for (int i = 1; i < 32; ++i)
+        if (ent[i] == ent[i - 1]) cont |= 1u << i;
+    return cont & valid & (valid << 1);
 }
 
 // run length of the entry opened at base i: 1 + the continuation bits that follow it
@@ -93,8 +154,8 @@ __device__ __forceinline__ uint32_t run_length(uint32_t cont, int i)
 // tile-level radix partition in shared memory, then one run per slice to HBM
 // ---------------------------------------------------------------------------
 struct ScatterSmem {
-    uint32_t cnt[kMaxBuckets];             // entries of this tile per slice
-    uint32_t fill[kMaxBuckets];            // second cursor: position inside the tile's run
+    uint32_t cnt[kMaxBuckets + 1];         // entries of this tile per slice (+1: dummy slot of non-emitting windows)
+    uint32_t fill[kMaxBuckets + 1];        // staging cursor per slice (starts at base[] after the claim; +1 dummy)
     uint32_t base[kMaxBuckets];            // exclusive scan of cnt
     unsigned long long gbase[kMaxBuckets]; // where this tile's run starts in the entry buffer
 };
@@ -118,6 +179,8 @@ __device__ __forceinline__ void scatter_claim(ScatterSmem& S, const BucketGeom& 
         const uint32_t total0 = __shfl_sync(0xffffffffu, i0, 31);
         S.base[b0] = i0 - c0;
         S.base[b1] = total0 + i1 - c1;
+        S.fill[b0] = i0 - c0;          // the staging cursor of a slice starts at its run's offset
+        S.fill[b1] = total0 + i1 - c1;
         if (c0) {
             if (off0 + c0 > geo.cap) { atomicMin(&st->limits[b0], off0); S.gbase[b0] = kOverflowRun; }
             else S.gbase[b0] = (unsigned long long)b0 * geo.cap + off0;
@@ -131,36 +194,47 @@ __device__ __forceinline__ void scatter_claim(ScatterSmem& S, const BucketGeom& 
 }
 
 // ---- count ----------------------------------------------------------------
+template <int KT>
 __global__ void __launch_bounds__(256, 3)
 bucket_scatter_count_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ maskC, int64_t w0, int64_t w1, int k,
                             BucketGeom geo, BucketState* __restrict__ st, uint32_t* __restrict__ entries, uint32_t* __restrict__ table)
 {
     __shared__ ScatterSmem S;
     __shared__ uint32_t stage[kTileEntries];
-    const uint32_t km = (1u << k) - 1u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *const cnt_base = S.cnt, *const fill_base = S.fill, *const stage_base = stage;
     const int64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (threadIdx.x < kMaxBuckets) { S.cnt[threadIdx.x] = 0u; S.fill[threadIdx.x] = 0u; }
+        if (threadIdx.x <= kMaxBuckets) S.cnt[threadIdx.x] = 0u;
         __syncthreads();
         const int64_t j = w0 + t * kTileWords + threadIdx.x;
-        uint32_t ent[32], start = 0u, cont = 0u;
+        uint32_t ent[32], valid = 0u, cont = 0u;
         if (j < w1) {
             const uint32_t mlo = __ldg(maskC + j);
-            if (mlo != 0u) word_windows<true>(__ldg(codes + j), __ldg(codes + j + 1), mlo, __ldg(maskC + j + 1), k, km, ent, start, cont);
+            if (mlo != 0u) {
+                uint32_t min_diff;
+                valid = window_valid_mask(mlo, __ldg(maskC + j + 1), KT ? KT : k);
+                word_indices<KT, true>(__ldg(codes + j), __ldg(codes + j + 1), k, ent, min_diff);
+                if (min_diff == 0u) cont = continuation_mask(ent, valid);
+            }
         }
+        const uint32_t start = valid & ~cont;
+        if (start != 0u) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if ((start >> i) & 1u) atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
+            for (int i = 0; i < 32; ++i) smem_inc_if(cnt_base, ent[i] >> kSliceBits, start & (1u << i));
+        }
         __syncthreads();
         scatter_claim(S, geo, st);
+        if (cont == 0u) { // no run in this word (the usual case): plain entries
+            if (start != 0u) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if ((start >> i) & 1u) {
-                const uint32_t b = ent[i] >> kSliceBits;
-                const uint32_t at = S.base[b] + atomicAdd(&S.fill[b], 1u);
-                stage[at] = (ent[i] & geo.low_mask) | ((run_length(cont, i) - 1u) << kSliceBits);
+                for (int i = 0; i < 32; ++i) smem_push_if(fill_base, ent[i] >> kSliceBits, stage_base, ent[i] & geo.low_mask, start & (1u << i));
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                smem_push_if(fill_base, ent[i] >> kSliceBits, stage_base, (ent[i] & geo.low_mask) | ((run_length(cont, i) - 1u) << kSliceBits), start & (1u << i));
+        }
         __syncthreads();
         for (int b = warp; b < geo.n_buckets; b += 8) { // one warp copies one slice's run: coalesced, no search
             const uint32_t n = S.cnt[b];
@@ -257,6 +331,7 @@ __device__ __forceinline__ bool abd_key(const FeatParams& P, uint32_t c, uint32_
 // slice for bucket_apply_feat_kernel.  Words that straddle a cloud boundary take the
 // direct path of featurize.cuh (rare: one word per cloud).  P.maskF is the cleaned
 // feature mask: dropped clouds and PG_READ_NOFEAT reads are already zero in it.
+template <int KT>
 __global__ void __launch_bounds__(256, 2)
 bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, BucketGeom geo, BucketState* __restrict__ st,
                            unsigned long long* __restrict__ entries)
@@ -265,8 +340,8 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
     __shared__ ScatterSmem S;
     uint32_t* stage_idx = smem;                                  // [kTileEntries]
     uint32_t* stage_row = smem + kTileEntries;                   // [kTileEntries]
-    uint32_t* bins = smem + 2 * kTileEntries;                    // [kSlots][td]  (TNF only)
-    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + kSlots * P.td);
+    uint32_t* bins = smem + 2 * kTileEntries;                    // [kSlots][td] + 1 dummy word (TNF only)
+    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + kSlots * P.td + 1);
     const int lut_n = 1 << (2 * P.tnf_k);
     for (int i = threadIdx.x; i < kSlots * P.td; i += blockDim.x) bins[i] = 0u;
     for (int i = threadIdx.x; i < lut_n; i += blockDim.x) lut_s[i] = P.lut[i];
@@ -276,10 +351,10 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
     const int64_t w_end = min(seg_w1, w_begin + P.words_per_cta);
     if (w_begin >= w_end) return;
 
-    const int k = P.table.k;
-    const uint32_t km = (1u << k) - 1u, tm = (1u << P.tnf_k) - 1u;
+    const int k = KT ? KT : P.table.k;
     const uint32_t tmask = (1u << (2 * P.tnf_k)) - 1u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *const cnt_base = S.cnt, *const fill_base = S.fill, *const stage_idx_base = stage_idx, *const stage_row_base = stage_row;
 
     int64_t g_cur = advance_group(P.gstart, P.n_groups, 0, w_begin * 32);
     int64_t tile = w_begin;
@@ -296,7 +371,7 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
             tile = max(tile + (int64_t)kTileWords, jump);
             continue;
         }
-        if (threadIdx.x < kMaxBuckets) { S.cnt[threadIdx.x] = 0u; S.fill[threadIdx.x] = 0u; }
+        if (threadIdx.x <= kMaxBuckets) S.cnt[threadIdx.x] = 0u;
         __syncthreads();
 
         const int64_t j = tile + threadIdx.x;
@@ -314,16 +389,26 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
                 row = __ldg(P.row_of_group + g);
                 if (row >= 0) {
                     const int64_t slot = g - g_lo;
-                    uint32_t* tnf_row = slot < kSlots ? bins + slot * P.td : P.tnf + (int64_t)row * P.td;
+                    const uint32_t tvalid = window_valid_mask(mlo, mhi, P.tnf_k);
+                    if (slot < kSlots) { // block-private bins; invalid windows hit the dummy word after the slots
+                        uint32_t* tnf_row = bins + slot * P.td;
+                        const uint32_t dummy = (uint32_t)(kSlots * P.td - slot * P.td);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t mw = __funnelshift_r(mlo, mhi, i);
-                        if ((mw & tm) == tm) {
+                        for (int i = 0; i < 32; ++i) {
                             const uint32_t w4 = (uint32_t)(i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & tmask;
-                            atomicAdd(tnf_row + lut_s[w4], 1u);
+                            atomicAdd(tnf_row + ((tvalid & (1u << i)) ? (uint32_t)lut_s[w4] : dummy), 1u);
                         }
+                    } else {
+                        uint32_t* tnf_row = P.tnf + (int64_t)row * P.td;
+                        for (int i = 0; i < 32; ++i)
+                            if (tvalid & (1u << i)) {
+                                const uint32_t w4 = (uint32_t)(i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & tmask;
+                                atomicAdd(tnf_row + lut_s[w4], 1u);
+                            }
                     }
-                    word_windows<false>(lo, hi, mlo, mhi, k, km, ent, start, cont);
+                    uint32_t unused;
+                    start = window_valid_mask(mlo, mhi, k);
+                    word_indices<KT, false>(lo, hi, k, ent, unused);
                 }
             } else {
                 // a cloud boundary inside the word: direct look-ups, abundance straight to the global row
@@ -343,19 +428,17 @@ bucket_scatter_feat_kernel(const FeatParams P, int64_t seg_w0, int64_t seg_w1, B
                 }
             }
         }
+        if (start != 0u) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if ((start >> i) & 1u) atomicAdd(&S.cnt[ent[i] >> kSliceBits], 1u);
+            for (int i = 0; i < 32; ++i) smem_inc_if(cnt_base, ent[i] >> kSliceBits, start & (1u << i));
+        }
         __syncthreads();
         scatter_claim(S, geo, st);
+        if (start != 0u) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if ((start >> i) & 1u) {
-                const uint32_t b = ent[i] >> kSliceBits;
-                const uint32_t at = S.base[b] + atomicAdd(&S.fill[b], 1u);
-                stage_idx[at] = ent[i] & geo.low_mask;
-                stage_row[at] = (uint32_t)row;
-            }
+            for (int i = 0; i < 32; ++i)
+                smem_push2_if(fill_base, ent[i] >> kSliceBits, stage_idx_base, stage_row_base, ent[i] & geo.low_mask, (uint32_t)row, start & (1u << i));
+        }
         __syncthreads();
         for (int b = warp; b < geo.n_buckets; b += 8) {
             const uint32_t n = S.cnt[b];

@@ -70,8 +70,8 @@ PG_HD uint64_t canonical_of_fwd(uint64_t v, int k)
 //            exactly one of them has bit k clear; take that one and squeeze the
 //            bit out: a bijection {v, rc(v)} -> [0, 4^k / 2).  Halves the table
 //            (k = 15: 2^29 counters = 2 GiB) and needs no min().
-// The class id is then SCRAMBLED by an invertible mixing function on its bit width
-// (multiply by an odd constant, xor-shift by half the width, multiply again).  The
+// The class id is then SCRAMBLED by an invertible map on its bit width (multiplication by
+// an odd constant mod 2^bits - Fibonacci hashing, whose high bits mix every input bit).  The
 // table is swept in contiguous slices (bucket.cuh); scrambling makes every slice
 // receive the same share of the k-mers whatever the base composition of the
 // genomes (an AT-rich community would otherwise fill some slices 2-4x more than
@@ -80,39 +80,31 @@ PG_HD uint64_t canonical_of_fwd(uint64_t v, int k)
 PG_HD uint64_t dense_entries(int k) { return (k & 1) ? (1ull << (2 * k - 1)) : (1ull << (2 * k)); }
 PG_HD int dense_bits(int k) { return (k & 1) ? 2 * k - 1 : 2 * k; }
 
-constexpr uint32_t kMixA = 0x9E3779B1u, kMixB = 0x85EBCA6Bu;
+constexpr uint32_t kMixA = 0x9E3779B1u; // odd: multiplication mod 2^bits is a bijection; the HIGH bits of the
+                                        // product (the slice number) depend on every bit of the class id
 constexpr uint32_t mod_inverse32(uint32_t a)
 {
     uint32_t x = a; // Newton: doubles the number of correct low bits each round (a*a = 1 mod 8)
     for (int i = 0; i < 5; ++i) x *= 2u - a * x;
     return x;
 }
-constexpr uint32_t kMixAInv = mod_inverse32(kMixA), kMixBInv = mod_inverse32(kMixB);
-static_assert(kMixA * kMixAInv == 1u && kMixB * kMixBInv == 1u, "modular inverses");
+constexpr uint32_t kMixAInv = mod_inverse32(kMixA);
+static_assert(kMixA * kMixAInv == 1u, "modular inverse");
 
 PG_HD uint32_t scramble_bits(uint32_t x, int bits)
 {
-    if (bits < 8) return x;
     const uint32_t m = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-    const int h = (bits + 1) >> 1;
-    x = (x * kMixA) & m;
-    x ^= x >> h;
-    return (x * kMixB) & m;
+    return (x * kMixA) & m;
 }
 PG_HD uint32_t unscramble_bits(uint32_t y, int bits)
 {
-    if (bits < 8) return y;
     const uint32_t m = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-    const int h = (bits + 1) >> 1;
-    y = (y * kMixBInv) & m;
-    y ^= y >> h; // 2h >= bits: the xor-shift is its own inverse
     return (y * kMixAInv) & m;
 }
 
-PG_HD uint32_t dense_index_of_window(uint32_t w, int k)
+// class id of the k-mer whose forward value is f and whose reverse complement is r
+PG_HD uint32_t dense_index_of_pair(uint32_t f, uint32_t r, int k)
 {
-    uint32_t f = fwd_of_window32(w, k);
-    uint32_t r = w ^ (0xAAAAAAAAu & (uint32_t)low_mask64(2 * k));
     uint32_t id;
     if (k & 1) {
         uint32_t x = ((f >> k) & 1u) ? r : f;
@@ -121,6 +113,11 @@ PG_HD uint32_t dense_index_of_window(uint32_t w, int k)
         id = f < r ? f : r;
     }
     return scramble_bits(id, dense_bits(k));
+}
+
+PG_HD uint32_t dense_index_of_window(uint32_t w, int k)
+{
+    return dense_index_of_pair(fwd_of_window32(w, k), w ^ (0xAAAAAAAAu & (uint32_t)low_mask64(2 * k)), k);
 }
 
 PG_HD uint64_t dense_index_of_fwd(uint64_t v, int k)
