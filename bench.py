@@ -202,18 +202,20 @@ def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows,
     if sliced:
         b["count_scatter"] = n_bytes * stream + 4.0 * entries_count
         b["count_apply"] = 4.0 * entries_count + 8.0 * windows_count      # u32 counter read-modify-write per window
-        b["feat_scatter"] = n_bytes * stream + 8.0 * windows_feat
-        b["feat_apply"] = 8.0 * windows_feat + 4.0 * windows_feat + out   # entry + u32 counter read per window, tallies out
+        b["tnf"] = n_bytes * stream + 4.0 * rows * td
+        b["feat_scatter"] = n_bytes * stream + 4.0 * windows_feat
+        b["feat_apply"] = 4.0 * windows_feat + 4.0 * windows_feat + 4.0 * rows * vs   # entry + u32 counter read per window, tallies out
     else:
         b["count_apply"] = n_bytes * stream + 8.0 * windows_count
         b["feat_apply"] = n_bytes * stream + 4.0 * windows_feat + out
     return b
 
 
-KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_count_kernel", "count_apply": "bucket_apply_count_kernel",
-                   "group": "flag_count/tile_scan/group_starts/row_assign kernels", "feat_scatter": "bucket_scatter_feat_kernel",
-                   "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
-STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_apply", 1), ("group", 2), ("feat_scatter", 7), ("feat_apply", 3), ("normalize", 4))
+KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,false>", "count_apply": "bucket_apply_count_kernel",
+                   "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
+                   "feat_scatter": "bucket_scatter_kernel<15,true>", "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
+STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
+               ("normalize", 4))
 
 
 def load_peaks():

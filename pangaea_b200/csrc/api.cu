@@ -20,6 +20,7 @@
 #include "scan.cuh"
 #include "synth.cuh"
 #include "table.cuh"
+#include "tnf.cuh"
 
 using namespace pg;
 
@@ -27,7 +28,7 @@ using namespace pg;
 // objects
 // ---------------------------------------------------------------------------
 // timing slots: one per kernel family (pg_timing_get `which`)
-enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_SLOTS = 8 };
+enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_SLOTS = 9 };
 
 struct pg_ctx {
     pg_params p;
@@ -49,8 +50,8 @@ struct pg_ctx {
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
-    int64_t seg_words = 1ll << 25; // words per segment of the L2-sliced path: 2^30 windows -> entry buffer <= 4 GiB (count) /
-                                   // 8 GiB (featurize); PG_SEG_WORDS overrides (tests force many segments on small inputs)
+    int64_t seg_words = 1ll << 25; // words per segment of the L2-sliced path: 2^30 windows -> entry buffer <= 6 GiB with the
+                                   // default slack; PG_SEG_WORDS overrides (tests force many segments on small inputs)
     std::string err;
     // timing
     struct Span { int which; cudaEvent_t a, b; };
@@ -246,7 +247,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaMalloc((void**)&ctx->d_bucket, sizeof(BucketState)));
     { const char* e = getenv("PG_REGION_SLACK"); if (e && atof(e) > 0) ctx->region_slack = atof(e); }
     { const char* e = getenv("PG_FORCE_DIRECT"); ctx->force_direct = e && e[0] == '1'; }
-    { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= kTileWords) ctx->seg_words = atoll(e) / kTileWords * kTileWords; }
+    { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
         ctx->n_slots = dense_entries(p->k);
@@ -258,8 +259,12 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     }
     CKC(cudaFuncSetAttribute(featurize_kernel<kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaFuncSetAttribute(featurize_kernel<kHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CKC(cudaFuncSetAttribute(bucket_scatter_feat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(tnf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CKC(cudaFuncSetAttribute(tnf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
 #undef CKC
     *out = ctx;
@@ -451,8 +456,8 @@ static int check_overflow(pg_ctx* ctx)
 static bool use_buckets(const pg_ctx* c)
 {
     if (c->mode != kDense || c->force_direct) return false;
-    const uint64_t nb = c->n_slots >> kSliceBits;
-    return nb >= 2 && nb <= (uint64_t)kMaxBuckets;
+    const uint64_t nb = c->n_slots >> kSliceBits; // entries carry 8 x index in 32 bits: index < 2^29
+    return nb >= 2 && nb <= (uint64_t)kMaxBuckets && dense_bits(c->p.k) <= 29;
 }
 
 static BucketGeom bucket_geom(const pg_ctx* ctx, int64_t seg_words)
@@ -465,23 +470,39 @@ static BucketGeom bucket_geom(const pg_ctx* ctx, int64_t seg_words)
     return geo;
 }
 
+// grid of a scatter launch: every resident CTA walks tiles with a grid stride
+template <bool FEAT>
+static int scatter_grid(pg_ctx* ctx, int k, int64_t n_tiles, int* grid_out)
+{
+    int occ = 1;
+    if (k == 15) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<15, FEAT>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<0, FEAT>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
+    if (occ < 1) return fail(ctx, PG_ERR_CUDA, "scatter kernel does not fit on this device");
+    *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ));
+    return PG_OK;
+}
+
 static int count_bucketed(pg_ctx* ctx, pg_batch* b)
 {
     const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
     const BucketGeom geo = bucket_geom(ctx, seg_words);
     uint32_t* entries;
     CK(dmalloc(ctx, &entries, (size_t)geo.cap * geo.n_buckets));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_count_kernel<15>, 256, 0));
+    ScatterParams Q;
+    Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
+    Q.entries = entries; Q.meta = nullptr; Q.table = ctx->counts;
+    const FeatParams none = {};
     for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
         const int64_t w1 = std::min(b->n_words, w0 + seg_words);
-        const int64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
+        Q.w0 = w0; Q.w1 = w1;
+        int grid = 1;
+        int rc = scatter_grid<false>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<false>::kTileWords - 1) / ScatterCfg<false>::kTileWords, &grid);
+        if (rc) { dfree(ctx, entries); return rc; }
         {
             Timed t(ctx, T_COUNT_SCATTER, 2);
             bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-            const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ);
-            if (ctx->p.k == 15) bucket_scatter_count_kernel<15><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, w0, w1, 15, geo, ctx->d_bucket, entries, ctx->counts);
-            else bucket_scatter_count_kernel<0><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, w0, w1, ctx->p.k, geo, ctx->d_bucket, entries, ctx->counts);
+            if (ctx->p.k == 15) bucket_scatter_kernel<15, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
+            else bucket_scatter_kernel<0, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
         }
         Timed t(ctx, T_COUNT, 1);
         bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
@@ -648,17 +669,18 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     CK(cudaSetDevice(ctx->p.device));
 
     int64_t* gstart = nullptr;
-    uint32_t* maskR = nullptr;
-    unsigned long long* feat_entries = nullptr;
+    uint32_t *maskR = nullptr, *wg = nullptr, *feat_entries = nullptr;
     unsigned long long* nofeat_len = nullptr;
     uint8_t *d_keep = nullptr, *emit = nullptr;
-    int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr;
+    int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr, *row_lb = nullptr, *feat_meta = nullptr;
+    const bool sliced = use_buckets(ctx);
     int64_t changes = 0, nofeat = 0, rows = 0;
     int rc = PG_OK;
     pg_features* f = nullptr;
     auto cleanup = [&]() {
         dfree(ctx, gstart); dfree(ctx, nofeat_len); dfree(ctx, d_keep); dfree(ctx, emit);
         dfree(ctx, row_of_group); dfree(ctx, group_of_row_full); dfree(ctx, maskR); dfree(ctx, feat_entries);
+        dfree(ctx, wg); dfree(ctx, row_lb); dfree(ctx, feat_meta);
     };
 #define CKF(call)                                                                                        \
     do {                                                                                                 \
@@ -672,25 +694,25 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
 
     // ---- grouping --------------------------------------------------------
     {
-        Timed t(ctx, T_GROUP, 10); // 3 scans x 2 kernels + starts + emit + rows + dropped-cloud mask
+        Timed t(ctx, T_GROUP, 11); // 3 scans x 2 kernels + starts + emit + rows + word -> cloud map (2)
         CKF(dmalloc(ctx, &gstart, (size_t)n_groups + 1));
         CKF(dmalloc(ctx, &nofeat_len, (size_t)n_groups));
         CKF(dmalloc(ctx, &d_keep, (size_t)n_groups));
         CKF(dmalloc(ctx, &emit, (size_t)n_groups));
         CKF(dmalloc(ctx, &row_of_group, (size_t)n_groups));
         CKF(dmalloc(ctx, &group_of_row_full, (size_t)n_groups));
+        CKF(dmalloc(ctx, &row_lb, (size_t)n_groups));
         CKF(cudaMemsetAsync(nofeat_len, 0, (size_t)n_groups * sizeof(unsigned long long), ctx->stream));
         CKF(cudaMemcpyAsync(d_keep, group_keep, (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
-        // working copy of the feature mask: NOFEAT reads and dropped clouds get cleared in it
-        CKF(dmalloc(ctx, &maskR, (size_t)b->n_words + 2));
-        CKF(cudaMemcpyAsync(maskR, b->maskF, ((size_t)b->n_words + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-
-        // PG_READ_NOFEAT reads are rare; when present their bases are masked out of maskF
+        // PG_READ_NOFEAT reads are rare; when present their bases are masked out of a working copy of maskF
         rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_NOFEAT, &tile_off, &nofeat);
         if (rc) { cleanup(); return rc; }
         dfree(ctx, tile_off);
-        if (nofeat)
+        if (nofeat) {
+            CKF(dmalloc(ctx, &maskR, (size_t)b->n_words + 2));
+            CKF(cudaMemcpyAsync(maskR, b->maskF, ((size_t)b->n_words + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
             clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, maskR);
+        }
 
         rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_CHANGE, &tile_off, &changes);
         if (rc) { cleanup(); return rc; }
@@ -714,10 +736,14 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
         if (rc) { cleanup(); return rc; }
         {
             const int64_t n_tiles = std::max<int64_t>(1, (n_groups + kScanTile - 1) / kScanTile);
-            row_assign_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(emit, n_groups, tile_off, row_of_group, group_of_row_full);
+            row_assign_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(emit, n_groups, tile_off, row_of_group, group_of_row_full, row_lb);
         }
         dfree(ctx, tile_off);
-        clear_dropped_groups_kernel<<<(int)std::min<int64_t>(n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(gstart, row_of_group, n_groups, maskR);
+        if (sliced && b->n_words) { // word -> cloud map of the streaming kernels
+            CKF(dmalloc(ctx, &wg, (size_t)b->n_words));
+            word_groups_kernel<false><<<grid_for(n_groups * 32, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(gstart, n_groups, b->n_bytes, wg);
+            word_groups_kernel<true><<<(int)std::min<int64_t>(n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(gstart, n_groups, b->n_bytes, wg);
+        }
         CKF(cudaGetLastError());
     }
 
@@ -737,8 +763,8 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     // ---- the pass over the bases -------------------------------------------
     if (rows && b->n_words) {
         FeatParams P;
-        P.codes = b->codes; P.maskF = maskR; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
-        P.gstart = gstart; P.n_groups = n_groups; P.row_of_group = row_of_group;
+        P.codes = b->codes; P.maskF = maskR ? maskR : b->maskF; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
+        P.gstart = gstart; P.n_groups = n_groups; P.row_of_group = row_of_group; P.wg = wg; P.row_lb = row_lb;
         P.tnf_k = ctx->p.tnf_k; P.vs = f->vs; P.td = f->td;
         P.ws = (uint32_t)ctx->p.window_size;
         const uint64_t clamp64 = (uint64_t)P.ws * (uint64_t)P.vs;
@@ -749,30 +775,42 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
         P.lut = ctx->d_lut;
         P.abd = f->abd_raw; P.tnf = f->tnf_raw;
         P.table = view(ctx);
-        if (use_buckets(ctx)) {
-            // ---- L2-sliced path: TNF + partition of (index, row) pairs, then slice-by-slice look-ups ----
+        if (sliced) {
+            // ---- L2-sliced path: TNF kernel, then partition of the window indices and slice-by-slice look-ups ----
+            {
+                const size_t smem_t = ((size_t)kSlots * ((size_t)1 << (2 * P.tnf_k)) + 2) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
+                const int64_t max_cta = (int64_t)ctx->sm_count * 8;
+                const int64_t n_cta = std::min<int64_t>(max_cta, (b->n_words + kTnfThreads - 1) / kTnfThreads);
+                int64_t wpc = (b->n_words + n_cta - 1) / n_cta;
+                wpc = (wpc + kTnfThreads - 1) / kTnfThreads * kTnfThreads;
+                P.words_per_cta = wpc;
+                const int grid = (int)((b->n_words + wpc - 1) / wpc);
+                Timed t(ctx, T_TNF, 1);
+                if (P.tnf_k == 4) tnf_kernel<4><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
+                else tnf_kernel<0><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
+            }
             const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
-            const BucketGeom geo = bucket_geom(ctx, seg_words);
+            BucketGeom geo = bucket_geom(ctx, seg_words);
+            geo.cap = (unsigned long long)((double)geo.cap * 1.08 / 32.0 + 1.0) * 32ull; // runs are padded to 32 entries
             CKF(dmalloc(ctx, &feat_entries, (size_t)geo.cap * geo.n_buckets));
-            const size_t smem_s = (size_t)2 * kTileEntries * sizeof(uint32_t) + ((size_t)kSlots * P.td + 2) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
-            int occ_s = 1;
-            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, bucket_scatter_feat_kernel<15>, 256, smem_s));
-            if (occ_s < 1) { cleanup(); pg_features_free(ctx, f); return fail(ctx, PG_ERR_INVALID, "tnf_k too large for shared memory"); }
+            CKF(dmalloc(ctx, &feat_meta, (size_t)geo.cap * geo.n_buckets / 32));
+            ScatterParams Q;
+            Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
+            Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts;
             for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
                 const int64_t w1 = std::min(b->n_words, w0 + seg_words);
-                const int64_t n_cta = std::min<int64_t>((int64_t)ctx->sm_count * occ_s, (w1 - w0 + kTileWords - 1) / kTileWords);
-                int64_t wpc = (w1 - w0 + n_cta - 1) / n_cta;
-                wpc = (wpc + kTileWords - 1) / kTileWords * kTileWords;
-                P.words_per_cta = wpc;
+                Q.w0 = w0; Q.w1 = w1;
+                int grid = 1;
+                rc = scatter_grid<true>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<true>::kTileWords - 1) / ScatterCfg<true>::kTileWords, &grid);
+                if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
                 {
                     Timed t(ctx, T_FEAT_SCATTER, 2);
                     bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-                    const int grid = (int)((w1 - w0 + wpc - 1) / wpc);
-                    if (ctx->p.k == 15) bucket_scatter_feat_kernel<15><<<grid, 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
-                    else bucket_scatter_feat_kernel<0><<<grid, 256, smem_s, ctx->stream>>>(P, w0, w1, geo, ctx->d_bucket, feat_entries);
+                    if (ctx->p.k == 15) bucket_scatter_kernel<15, true><<<grid, ScatterCfg<true>::kThreads, sizeof(ScatterSmem<true>), ctx->stream>>>(Q, P);
+                    else bucket_scatter_kernel<0, true><<<grid, ScatterCfg<true>::kThreads, sizeof(ScatterSmem<true>), ctx->stream>>>(Q, P);
                 }
                 Timed t(ctx, T_FEAT, 1);
-                bucket_apply_feat_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, geo, ctx->d_bucket, P);
+                bucket_apply_feat_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, feat_meta, geo, ctx->d_bucket, P);
             }
             CKF(cudaGetLastError());
             cleanup();

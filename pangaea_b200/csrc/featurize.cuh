@@ -39,6 +39,8 @@ struct FeatParams {
     const int64_t* gstart;      // n_groups + 1
     int64_t n_groups;
     const int32_t* row_of_group;
+    const uint32_t* wg;         // n_words: cloud of base 32 j | kWordMixed (scan.cuh) - sliced path and tnf.cuh
+    const int32_t* row_lb;      // n_groups: rows emitted before cloud g
     int32_t tnf_k, vs, td;
     uint32_t ws, clamp;         // clamp = min(ws * vs, 2^32-1): counts >= clamp fall outside the histogram
     uint32_t magic;             // ceil(2^32 / ws) when use_magic

@@ -138,7 +138,7 @@ __global__ void group_emit_kernel(const int64_t* __restrict__ gstart, const unsi
 // pass 3 (clouds): row numbers in file order
 __global__ void __launch_bounds__(kScanThreads)
 row_assign_kernel(const uint8_t* __restrict__ emit, int64_t n_groups, const int32_t* __restrict__ tile_off,
-                  int32_t* __restrict__ row_of_group, int32_t* __restrict__ group_of_row)
+                  int32_t* __restrict__ row_of_group, int32_t* __restrict__ group_of_row, int32_t* __restrict__ row_lb)
 {
     int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint8_t f[kScanItems];
@@ -154,12 +154,43 @@ row_assign_kernel(const uint8_t* __restrict__ emit, int64_t n_groups, const int3
     for (int i = 0; i < kScanItems; ++i) {
         int64_t g = base + i;
         if (g >= n_groups) break;
+        row_lb[g] = row; // rows emitted before cloud g: a lower bound for the row of every later cloud
         if (f[i]) {
             row_of_group[g] = row;
             group_of_row[row] = (int32_t)g;
             ++row;
         } else {
             row_of_group[g] = -1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// word -> cloud map for the streaming kernels (bucket.cuh, tnf.cuh): wg[j] = cloud of base
+// 32 j, with kWordMixed set when another cloud starts inside the word (one word per cloud:
+// those take a per-position slow path).  Filled per cloud, so the hot kernels never search
+// gstart.  BIG = false: one warp per cloud, clouds of more than kBigCloudWords words are left
+// to the BIG = true launch (one block per cloud; the unbarcoded tail can be millions of words).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kWordMixed = 0x80000000u;
+constexpr int64_t kBigCloudWords = 8192;
+
+template <bool BIG>
+__global__ void __launch_bounds__(256)
+word_groups_kernel(const int64_t* __restrict__ gstart, int64_t n_groups, int64_t n_bytes, uint32_t* __restrict__ wg)
+{
+    const int lane = BIG ? threadIdx.x : (threadIdx.x & 31);
+    const int step = BIG ? blockDim.x : 32;
+    const int64_t first = BIG ? blockIdx.x : (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int64_t stride = BIG ? gridDim.x : (((int64_t)gridDim.x * blockDim.x) >> 5);
+    for (int64_t g = first; g < n_groups; g += stride) {
+        const int64_t lo = __ldg(gstart + g), hi = __ldg(gstart + g + 1);
+        if (lo >= hi) continue;
+        const int64_t w_first = (lo + 31) >> 5, w_last = (hi - 1) >> 5; // words whose first base lies in [lo, hi)
+        if (((w_last - w_first + 1) > kBigCloudWords) != BIG) continue;
+        for (int64_t w = w_first + lane; w <= w_last; w += step) {
+            const bool mixed = (w == w_last) && hi < min((w + 1) << 5, n_bytes);
+            wg[w] = (uint32_t)g | (mixed ? kWordMixed : 0u);
         }
     }
 }

@@ -1,0 +1,121 @@
+// tnf.cuh - per-cloud tetranucleotide (tnf_k-mer) tallies of the sliced path.
+//
+// Replaces bin/count_tnf's countKmer (src/cpptools/count_tnf.cpp:78-113: ++map[canonical
+// 4-mer] per valid window, columns in ascending canonical-code order, :138-164).
+//
+// Streaming kernel over the packed bases, one 32-base word per thread.  The hot loop does no
+// canonicalisation at all: the 2 tnf_k-bit window code as it sits in the stream IS the bin
+// (4^tnf_k block-private shared-memory bins per cloud slot); a window and its reverse
+// complement are folded into their common column (lut) only when a cloud's bins leave shared
+// memory - once per cloud per CTA, not once per base.  Invalid windows hit a dummy bin so the
+// 32 shared atomics of a word are issued without divergence.
+//
+// A CTA owns a contiguous range of words and keeps the bins of the clouds under its cursor
+// (kSlots of them; clouds much smaller than a tile overflow to global reductions).  Words
+// that hold a cloud boundary (scan.cuh: kWordMixed, one per cloud) resolve the cloud per
+// position and go straight to the global matrix.
+//
+// Bound: shared-memory atomic throughput (one per base; profiles/microbench_r01.txt:
+// ~1.7-2.3 T/s) - HBM traffic is 0.375 B/base in, 4 * tnf_dim B per row out.
+#pragma once
+#include "bucket.cuh"
+
+namespace pg {
+
+constexpr int kTnfThreads = 256;
+
+template <int TK>
+__global__ void __launch_bounds__(kTnfThreads)
+tnf_kernel(const FeatParams P)
+{
+    extern __shared__ uint32_t smem[];
+    const int tk = TK ? TK : P.tnf_k;
+    const int nb = 1 << (2 * tk);                                  // raw bins per slot
+    uint32_t* bins = smem;                                         // [kSlots][nb] + 1 dummy
+    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + kSlots * nb + 1);
+    for (int i = threadIdx.x; i < kSlots * nb + 1; i += blockDim.x) bins[i] = 0u;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) lut_s[i] = P.lut[i];
+    __syncthreads();
+
+    const int64_t w_begin = (int64_t)blockIdx.x * P.words_per_cta;
+    const int64_t w_end = min(P.n_words, w_begin + P.words_per_cta);
+    if (w_begin >= w_end) return;
+    const uint32_t tmask = (uint32_t)nb - 1u;
+    const uint32_t dummy = (uint32_t)(kSlots * nb);
+
+    for (int64_t tile = w_begin; tile < w_end; tile += kTnfThreads) {
+        const int64_t tile_end = min(tile + (int64_t)kTnfThreads, w_end);
+        const uint32_t g_lo = __ldg(P.wg + tile) & ~kWordMixed;
+        const uint32_t g_hi = __ldg(P.wg + tile_end - 1) & ~kWordMixed; // clouds of the uniform words: g_lo .. g_hi
+        const int64_t j = tile + threadIdx.x;
+        uint32_t mlo = 0u;
+        if (j < tile_end) mlo = __ldg(P.maskF + j);
+        if (mlo != 0u) {
+            const uint32_t gw = __ldg(P.wg + j);
+            const uint32_t g = gw & ~kWordMixed;
+            const uint32_t mhi = __ldg(P.maskF + j + 1);
+            const uint32_t tvalid = window_valid_mask(mlo, mhi, tk);
+            if (!(gw & kWordMixed)) {
+                const int32_t row = __ldg(P.row_of_group + g);
+                if (row >= 0 && tvalid != 0u) {
+                    const uint64_t lo = __ldg(P.codes + j), hi = __ldg(P.codes + j + 1);
+                    const uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi;
+                    const uint32_t slot = g - g_lo;
+                    if (slot < (uint32_t)kSlots) { // block-private bins
+                        uint32_t* my = bins + slot * nb;
+                        const uint32_t dmy = dummy - slot * nb;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t u = i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32)));
+                            atomicAdd(my + ((tvalid & (1u << i)) ? (u & tmask) : dmy), 1u);
+                        }
+                    } else { // more clouds in this tile than slots
+                        uint32_t* tnf_row = P.tnf + (int64_t)row * P.td;
+                        for (int i = 0; i < 32; ++i)
+                            if (tvalid & (1u << i)) {
+                                const uint32_t u = (uint32_t)(i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo);
+                                atomicAdd(tnf_row + lut_s[u & tmask], 1u);
+                            }
+                    }
+                }
+            } else if (tvalid != 0u) {
+                // a cloud boundary inside the word: resolve the cloud per position
+                const uint64_t lo = __ldg(P.codes + j), hi = __ldg(P.codes + j + 1);
+                int64_t gg = g;
+                int64_t next_start = __ldg(P.gstart + gg + 1);
+                int32_t row = __ldg(P.row_of_group + gg);
+                for (int i = 0; i < 32; ++i) {
+                    const int64_t q = j * 32 + i;
+                    while (gg + 1 < P.n_groups && q >= next_start) {
+                        ++gg;
+                        next_start = __ldg(P.gstart + gg + 1);
+                        row = __ldg(P.row_of_group + gg);
+                    }
+                    if (row < 0 || !((tvalid >> i) & 1u)) continue;
+                    const uint32_t u = (uint32_t)(i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo);
+                    atomicAdd(P.tnf + (int64_t)row * P.td + lut_s[u & tmask], 1u);
+                }
+            }
+        }
+        __syncthreads();
+
+        // slot 0 stays in shared memory while the next tile continues the same single cloud
+        const bool carry = g_hi == g_lo && tile_end < w_end && (__ldg(P.wg + tile_end) & ~kWordMixed) == g_lo;
+        if (!carry) {
+            const uint32_t ns = min((uint32_t)kSlots, g_hi - g_lo + 1u);
+            for (uint32_t s = 0; s < ns; ++s) {
+                const int32_t row = __ldg(P.row_of_group + g_lo + s);
+                if (row < 0) continue;
+                uint32_t* src = bins + s * nb;
+                uint32_t* dst = P.tnf + (int64_t)row * P.td;
+                for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                    const uint32_t v = src[b];
+                    if (v) { atomicAdd(dst + lut_s[b], v); src[b] = 0u; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace pg
