@@ -201,7 +201,8 @@ def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows,
     b = {"pack": n_bytes * (1.0 + 0.25 + 2 * 0.125), "normalize": 2 * out}
     if sliced:
         b["count_scatter"] = n_bytes * stream + 4.0 * entries_count
-        b["count_apply"] = 4.0 * entries_count + 8.0 * windows_count      # u32 counter read-modify-write per window
+        b["count_split"] = 4.0 * entries_count + 2.0 * entries_count       # second partition level: u32 in, u16 out
+        b["count_apply"] = 2.0 * entries_count + 8.0 * windows_count      # entry + u32 counter read-modify-write per window
         b["tnf"] = n_bytes * stream + 4.0 * rows * td
         b["feat_scatter"] = n_bytes * stream + 4.0 * windows_feat
         b["feat_apply"] = 4.0 * windows_feat + 4.0 * windows_feat + 4.0 * rows * vs   # entry + u32 counter read per window, tallies out
@@ -211,10 +212,10 @@ def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows,
     return b
 
 
-KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,false>", "count_apply": "bucket_apply_count_kernel",
-                   "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
+KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,false>", "count_split": "bucket_split_kernel",
+                   "count_apply": "sub_apply_kernel", "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
                    "feat_scatter": "bucket_scatter_kernel<15,true>", "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
-STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
+STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_split", 9), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
                ("normalize", 4))
 
 

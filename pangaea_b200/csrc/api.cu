@@ -13,6 +13,7 @@
 #include "../../include/pangaea_b200.h"
 #include "bucket.cuh"
 #include "count.cuh"
+#include "count2.cuh"
 #include "featurize.cuh"
 #include "kmer.cuh"
 #include "normalize.cuh"
@@ -28,7 +29,7 @@ using namespace pg;
 // objects
 // ---------------------------------------------------------------------------
 // timing slots: one per kernel family (pg_timing_get `which`)
-enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_SLOTS = 9 };
+enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_COUNT_SPLIT = 9, T_SLOTS = 10 };
 
 struct pg_ctx {
     pg_params p;
@@ -50,6 +51,8 @@ struct pg_ctx {
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
+    bool count_l2 = false;       // PG_COUNT_L2=1: apply the count entries with L2 atomics instead of the shared-memory sub-slices (A/B)
+    int64_t count_seg_words = 1ll << 26; // segment of the count pass (2^31 windows: 13 GB of u32 + 6 GB of u16 entries); PG_SEG_WORDS overrides
     int64_t seg_words = 1ll << 25; // words per segment of the L2-sliced path: 2^30 windows -> entry buffer <= 6 GiB with the
                                    // default slack; PG_SEG_WORDS overrides (tests force many segments on small inputs)
     std::string err;
@@ -247,7 +250,8 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaMalloc((void**)&ctx->d_bucket, sizeof(BucketState)));
     { const char* e = getenv("PG_REGION_SLACK"); if (e && atof(e) > 0) ctx->region_slack = atof(e); }
     { const char* e = getenv("PG_FORCE_DIRECT"); ctx->force_direct = e && e[0] == '1'; }
-    { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
+    { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = ctx->count_seg_words = atoll(e) / 512 * 512; }
+    { const char* e = getenv("PG_COUNT_L2"); ctx->count_l2 = e && e[0] == '1'; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
         ctx->n_slots = dense_entries(p->k);
@@ -263,6 +267,8 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
+    CKC(cudaFuncSetAttribute(sub_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubWords * 4 + 16));
     CKC(cudaFuncSetAttribute(tnf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CKC(cudaFuncSetAttribute(tnf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -484,10 +490,31 @@ static int scatter_grid(pg_ctx* ctx, int k, int64_t n_tiles, int* grid_out)
 
 static int count_bucketed(pg_ctx* ctx, pg_batch* b)
 {
-    const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
+    const bool two_level = !ctx->count_l2;
+    const int64_t seg_words = std::min<int64_t>(b->n_words, two_level ? ctx->count_seg_words : ctx->seg_words);
     const BucketGeom geo = bucket_geom(ctx, seg_words);
-    uint32_t* entries;
+    uint32_t* entries = nullptr;
+    uint16_t* entries2 = nullptr;
+    SubGeom sg = {};
+    SubState ss = {};
+    auto cleanup = [&]() { dfree(ctx, entries); dfree(ctx, entries2); dfree(ctx, ss.cursors); dfree(ctx, ss.limits); dfree(ctx, ss.item_base); };
     CK(dmalloc(ctx, &entries, (size_t)geo.cap * geo.n_buckets));
+    int split_grid = 1;
+    if (two_level) {
+        sg.n_sub = geo.n_buckets * kSubFan;
+        const double mean = (double)seg_words * 32.0 / sg.n_sub;
+        // runs are padded to 8 entries: + 3.5 entries per run of 64 x (valid fraction) on average
+        sg.cap = (uint32_t)std::min<double>(4.0e9, std::max(64.0, std::ceil(mean * 1.08 * ctx->region_slack / 8.0) * 8.0));
+        sg.chunk = (uint32_t)std::max<double>(131072.0, std::ceil(2.0 * mean / 8.0) * 8.0);
+        cudaError_t e = dmalloc(ctx, &entries2, (size_t)sg.cap * sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &ss.cursors, (size_t)sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &ss.limits, (size_t)sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &ss.item_base, (size_t)sg.n_sub + 1);
+        int occ = 1;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_split_kernel, kSplitThreads, sizeof(SplitSmem));
+        if (e != cudaSuccess) { cleanup(); return fail(ctx, PG_ERR_CUDA, std::string("count_bucketed: ") + cudaGetErrorString(e)); }
+        split_grid = ctx->sm_count * std::max(occ, 1);
+    }
     ScatterParams Q;
     Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
     Q.entries = entries; Q.meta = nullptr; Q.table = ctx->counts;
@@ -497,18 +524,29 @@ static int count_bucketed(pg_ctx* ctx, pg_batch* b)
         Q.w0 = w0; Q.w1 = w1;
         int grid = 1;
         int rc = scatter_grid<false>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<false>::kTileWords - 1) / ScatterCfg<false>::kTileWords, &grid);
-        if (rc) { dfree(ctx, entries); return rc; }
+        if (rc) { cleanup(); return rc; }
         {
             Timed t(ctx, T_COUNT_SCATTER, 2);
             bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
             if (ctx->p.k == 15) bucket_scatter_kernel<15, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
             else bucket_scatter_kernel<0, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
         }
-        Timed t(ctx, T_COUNT, 1);
-        bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
+        if (two_level) {
+            {
+                Timed t(ctx, T_COUNT_SPLIT, 2);
+                sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(ss, sg);
+                bucket_split_kernel<<<split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(entries, geo, ctx->d_bucket, sg, ss, entries2, ctx->counts);
+            }
+            Timed t(ctx, T_COUNT, 2);
+            sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(ss, sg);
+            sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(entries2, sg, ss, ctx->counts);
+        } else {
+            Timed t(ctx, T_COUNT, 1);
+            bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
+        }
     }
     CK(cudaGetLastError());
-    dfree(ctx, entries);
+    cleanup();
     return PG_OK;
 }
 

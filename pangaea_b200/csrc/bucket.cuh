@@ -54,6 +54,9 @@ struct ScatterCfg {
     // staging slots per slice per tile: mean = 32 * kThreads / 64 (128 / 256) + > 5 sigma of the binomial
     static constexpr int kStageCap = FEAT ? 352 : 192;
     static constexpr int kMinCtas = FEAT ? 2 : 4;
+    // runs are padded with kInvalidEntry to a multiple of this, so that they start 16 B aligned and are copied
+    // out with 128-bit stores (feature runs: 32, because every aligned group of 32 entries shares one base row)
+    static constexpr uint32_t kRunPad = FEAT ? 32u : 4u;
 };
 
 struct BucketGeom {
@@ -309,7 +312,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 const uint32_t c = cnt[b];
                 const bool over = c > (uint32_t)CAP;
                 const uint32_t n = over ? 0u : c;
-                const uint32_t claim = FEAT ? ((n + 31u) & ~31u) : n;
+                const uint32_t claim = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
                 unsigned long long gb = kOverflowRun;
                 if (claim) {
                     const unsigned long long off = atomicAdd(&Q.st->cursors[b], (unsigned long long)claim);
@@ -331,22 +334,17 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             const uint32_t* src = stage + b * CAP;
             const unsigned long long gb = S.gbase[b];
             if (gb != kOverflowRun) {
-                if (FEAT) {
-                    const uint32_t n_pad = (n + 31u) & ~31u;
-                    uint4* dst = reinterpret_cast<uint4*>(Q.entries + gb);
-                    for (uint32_t e = 4u * lane; e < n_pad; e += 128u) {
-                        uint4 v = *reinterpret_cast<const uint4*>(src + e);
-                        if (e + 0u >= n) v.x = kInvalidEntry;
-                        if (e + 1u >= n) v.y = kInvalidEntry;
-                        if (e + 2u >= n) v.z = kInvalidEntry;
-                        if (e + 3u >= n) v.w = kInvalidEntry;
-                        __stcs(dst + (e >> 2), v);
-                    }
-                    if ((uint32_t)lane < (n_pad >> 5)) Q.meta[(gb >> 5) + lane] = tile_row0;
-                } else {
-                    uint32_t* dst = Q.entries + gb;
-                    for (uint32_t e = lane; e < n; e += 32) __stcs(dst + e, src[e]);
+                const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
+                uint4* dst = reinterpret_cast<uint4*>(Q.entries + gb);
+                for (uint32_t e = 4u * lane; e < n_pad; e += 128u) {
+                    uint4 v = *reinterpret_cast<const uint4*>(src + e);
+                    if (e + 0u >= n) v.x = kInvalidEntry;
+                    if (e + 1u >= n) v.y = kInvalidEntry;
+                    if (e + 2u >= n) v.z = kInvalidEntry;
+                    if (e + 3u >= n) v.w = kInvalidEntry;
+                    __stcs(dst + (e >> 2), v);
                 }
+                if (FEAT && (uint32_t)lane < (n_pad >> 5)) Q.meta[(gb >> 5) + lane] = tile_row0;
             } else if (FEAT) { // region full: look the run up here (whole warp stays in the loop for the reduction)
                 for (uint32_t e0 = 0; e0 < n; e0 += 32) {
                     const uint32_t e = e0 + lane;
