@@ -36,6 +36,7 @@ struct pg_ctx {
     int td = 0;
     int mode = kDense;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // H2D of the pipelined upload (pg_extract_features)
     int sm_count = 148;
     // table
     uint32_t* counts = nullptr;
@@ -53,8 +54,8 @@ struct pg_ctx {
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
     bool count_l2 = false;       // PG_COUNT_L2=1: apply the count entries with L2 atomics instead of the shared-memory sub-slices (A/B)
     int64_t count_seg_words = 1ll << 26; // segment of the count pass (2^31 windows: 13 GB of u32 + 6 GB of u16 entries); PG_SEG_WORDS overrides
-    int64_t seg_words = 1ll << 25; // words per segment of the L2-sliced path: 2^30 windows -> entry buffer <= 6 GiB with the
-                                   // default slack; PG_SEG_WORDS overrides (tests force many segments on small inputs)
+    int64_t seg_words = 1ll << 26; // words per segment of the featurize pass: 2^31 windows -> 14 GB of u32 entries with the default
+                                   // slack; PG_SEG_WORDS / PG_FEAT_SEG_WORDS override (tests force many segments on small inputs)
     std::string err;
     // timing
     struct Span { int which; cudaEvent_t a, b; };
@@ -235,6 +236,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     } while (0)
     CKC(cudaSetDevice(p->device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     {   // keep freed blocks in the pool: steady-state steps allocate without touching the driver
         cudaMemPool_t pool;
@@ -252,6 +254,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     { const char* e = getenv("PG_FORCE_DIRECT"); ctx->force_direct = e && e[0] == '1'; }
     { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = ctx->count_seg_words = atoll(e) / 512 * 512; }
     { const char* e = getenv("PG_COUNT_L2"); ctx->count_l2 = e && e[0] == '1'; }
+    { const char* e = getenv("PG_FEAT_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
         ctx->n_slots = dense_entries(p->k);
@@ -281,11 +284,13 @@ extern "C" void pg_destroy(pg_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->p.device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
     cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -335,19 +340,33 @@ extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* la
 // ---------------------------------------------------------------------------
 // batches
 // ---------------------------------------------------------------------------
-static int pack_batch(pg_ctx* ctx, pg_batch* b)
+static int alloc_packed(pg_ctx* ctx, pg_batch* b)
 {
     b->n_words = (b->n_bytes + 31) / 32;
     CK(dmalloc(ctx, &b->codes, (size_t)b->n_words + 2));
     CK(dmalloc(ctx, &b->maskF, (size_t)b->n_words + 2));
     CK(dmalloc(ctx, &b->maskC, (size_t)b->n_words + 2));
+    return PG_OK;
+}
+
+// pack words [w_begin, w_end) (w_end = n_words + 2 covers the two zeroed pad words)
+static int pack_range(pg_ctx* ctx, pg_batch* b, int64_t w_begin, int64_t w_end)
+{
+    if (w_end <= w_begin) return PG_OK;
     {
         Timed t(ctx, T_PACK, 1);
-        pack_kernel<<<grid_for(b->n_words + 2, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
-            b->seq, b->qual, b->n_bytes, b->n_words, (uint32_t)ctx->p.min_qual_char, b->codes, b->maskF, b->maskC);
+        pack_kernel<<<grid_for(w_end - w_begin, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            b->seq, b->qual, b->n_bytes, w_begin, w_end, (uint32_t)ctx->p.min_qual_char, b->codes, b->maskF, b->maskC);
     }
     CK(cudaGetLastError());
     return PG_OK;
+}
+
+static int pack_batch(pg_ctx* ctx, pg_batch* b)
+{
+    int rc = alloc_packed(ctx, b);
+    if (rc) return rc;
+    return pack_range(ctx, b, 0, b->n_words + 2);
 }
 
 static int check_reads(pg_ctx* ctx, const pg_reads* r)
@@ -359,15 +378,9 @@ static int check_reads(pg_ctx* ctx, const pg_reads* r)
     return PG_OK;
 }
 
-extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
+// device buffers of a host batch (no copies yet)
+static int alloc_batch(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
 {
-    int rc = check_reads(ctx, h);
-    if (rc) return rc;
-    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
-    *out = nullptr;
-    if (h->n_reads > 0 && (h->read_off[0] != 0 || h->read_off[h->n_reads] != h->n_bytes))
-        return fail(ctx, PG_ERR_INVALID, "read_off must start at 0 and end at n_bytes");
-    CK(cudaSetDevice(ctx->p.device));
     pg_batch* b = new pg_batch();
     b->owns = true;
     b->n_reads = h->n_reads;
@@ -377,16 +390,40 @@ extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
               dmalloc(ctx, &b->read_flag, (size_t)h->n_reads) == cudaSuccess;
     const bool want_q = ctx->p.min_qual_char && h->qual;
     if (ok && want_q) ok = dmalloc(ctx, &b->qual, padded) == cudaSuccess;
-    if (!ok) { pg_batch_free(ctx, b); return fail(ctx, PG_ERR_CUDA, "pg_batch_upload: device allocation failed"); }
+    if (ok) ok = alloc_packed(ctx, b) == PG_OK;
+    if (!ok) { pg_batch_free(ctx, b); return fail(ctx, PG_ERR_CUDA, "device allocation of the read batch failed"); }
+    *out = b;
+    return PG_OK;
+}
+
+static int check_host_batch(pg_ctx* ctx, const pg_reads* h)
+{
+    int rc = check_reads(ctx, h);
+    if (rc) return rc;
+    if (h->n_reads > 0 && (h->read_off[0] != 0 || h->read_off[h->n_reads] != h->n_bytes))
+        return fail(ctx, PG_ERR_INVALID, "read_off must start at 0 and end at n_bytes");
+    return PG_OK;
+}
+
+extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
+{
+    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
+    *out = nullptr;
+    int rc = check_host_batch(ctx, h);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->p.device));
+    pg_batch* b = nullptr;
+    rc = alloc_batch(ctx, h, &b);
+    if (rc) return rc;
     if (h->n_reads) {
         cudaMemcpyAsync(b->seq, h->seq, (size_t)h->n_bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (want_q) cudaMemcpyAsync(b->qual, h->qual, (size_t)h->n_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (b->qual) cudaMemcpyAsync(b->qual, h->qual, (size_t)h->n_bytes, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(b->read_off, h->read_off, ((size_t)h->n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(b->read_flag, h->read_flag, (size_t)h->n_reads, cudaMemcpyHostToDevice, ctx->stream);
     } else {
         cudaMemsetAsync(b->read_off, 0, sizeof(int64_t), ctx->stream);
     }
-    rc = pack_batch(ctx, b);
+    rc = pack_range(ctx, b, 0, b->n_words + 2);
     if (rc == PG_OK && cudaGetLastError() != cudaSuccess) rc = fail(ctx, PG_ERR_CUDA, "pg_batch_upload: copy failed");
     if (rc) { pg_batch_free(ctx, b); return rc; }
     *out = b;
@@ -488,66 +525,90 @@ static int scatter_grid(pg_ctx* ctx, int k, int64_t n_tiles, int* grid_out)
     return PG_OK;
 }
 
-static int count_bucketed(pg_ctx* ctx, pg_batch* b)
-{
-    const bool two_level = !ctx->count_l2;
-    const int64_t seg_words = std::min<int64_t>(b->n_words, two_level ? ctx->count_seg_words : ctx->seg_words);
-    const BucketGeom geo = bucket_geom(ctx, seg_words);
-    uint32_t* entries = nullptr;
-    uint16_t* entries2 = nullptr;
+// buffers and geometry of the sliced count pass, set up once per batch; segments are then
+// counted one by one (pg_extract_features interleaves them with the upload)
+struct CountPlan {
+    bool two_level = false;
+    int64_t seg_words = 0;
+    BucketGeom geo = {};
     SubGeom sg = {};
     SubState ss = {};
-    auto cleanup = [&]() { dfree(ctx, entries); dfree(ctx, entries2); dfree(ctx, ss.cursors); dfree(ctx, ss.limits); dfree(ctx, ss.item_base); };
-    CK(dmalloc(ctx, &entries, (size_t)geo.cap * geo.n_buckets));
+    uint32_t* entries = nullptr;
+    uint16_t* entries2 = nullptr;
     int split_grid = 1;
-    if (two_level) {
-        sg.n_sub = geo.n_buckets * kSubFan;
-        const double mean = (double)seg_words * 32.0 / sg.n_sub;
+};
+
+static void count_plan_free(pg_ctx* ctx, CountPlan& P)
+{
+    dfree(ctx, P.entries); dfree(ctx, P.entries2); dfree(ctx, P.ss.cursors); dfree(ctx, P.ss.limits); dfree(ctx, P.ss.item_base);
+    P = CountPlan();
+}
+
+static int count_plan_init(pg_ctx* ctx, int64_t n_words, CountPlan& P)
+{
+    P.two_level = !ctx->count_l2;
+    P.seg_words = std::max<int64_t>(1, std::min<int64_t>(n_words, P.two_level ? ctx->count_seg_words : ctx->seg_words));
+    P.geo = bucket_geom(ctx, P.seg_words);
+    cudaError_t e = dmalloc(ctx, &P.entries, (size_t)P.geo.cap * P.geo.n_buckets);
+    if (e == cudaSuccess && P.two_level) {
+        P.sg.n_sub = P.geo.n_buckets * kSubFan;
+        const double mean = (double)P.seg_words * 32.0 / P.sg.n_sub;
         // runs are padded to 8 entries: + 3.5 entries per run of 64 x (valid fraction) on average
-        sg.cap = (uint32_t)std::min<double>(4.0e9, std::max(64.0, std::ceil(mean * 1.08 * ctx->region_slack / 8.0) * 8.0));
-        sg.chunk = (uint32_t)std::max<double>(131072.0, std::ceil(2.0 * mean / 8.0) * 8.0);
-        cudaError_t e = dmalloc(ctx, &entries2, (size_t)sg.cap * sg.n_sub);
-        if (e == cudaSuccess) e = dmalloc(ctx, &ss.cursors, (size_t)sg.n_sub);
-        if (e == cudaSuccess) e = dmalloc(ctx, &ss.limits, (size_t)sg.n_sub);
-        if (e == cudaSuccess) e = dmalloc(ctx, &ss.item_base, (size_t)sg.n_sub + 1);
+        P.sg.cap = (uint32_t)std::min<double>(4.0e9, std::max(64.0, std::ceil(mean * 1.08 * ctx->region_slack / 8.0) * 8.0));
+        P.sg.chunk = (uint32_t)std::max<double>(131072.0, std::ceil(2.0 * mean / 8.0) * 8.0);
+        e = dmalloc(ctx, &P.entries2, (size_t)P.sg.cap * P.sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.cursors, (size_t)P.sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.limits, (size_t)P.sg.n_sub);
+        if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.item_base, (size_t)P.sg.n_sub + 1);
         int occ = 1;
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_split_kernel, kSplitThreads, sizeof(SplitSmem));
-        if (e != cudaSuccess) { cleanup(); return fail(ctx, PG_ERR_CUDA, std::string("count_bucketed: ") + cudaGetErrorString(e)); }
-        split_grid = ctx->sm_count * std::max(occ, 1);
+        P.split_grid = ctx->sm_count * std::max(occ, 1);
     }
+    if (e != cudaSuccess) { count_plan_free(ctx, P); return fail(ctx, PG_ERR_CUDA, std::string("count pass: ") + cudaGetErrorString(e)); }
+    return PG_OK;
+}
+
+// count the windows that start in words [w0, w1) (w1 - w0 <= plan.seg_words); words w1, w1 + 1 must be packed too
+static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int64_t w1)
+{
     ScatterParams Q;
-    Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
-    Q.entries = entries; Q.meta = nullptr; Q.table = ctx->counts;
+    Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = P.geo; Q.st = ctx->d_bucket;
+    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts;
+    Q.w0 = w0; Q.w1 = w1;
     const FeatParams none = {};
-    for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
-        const int64_t w1 = std::min(b->n_words, w0 + seg_words);
-        Q.w0 = w0; Q.w1 = w1;
-        int grid = 1;
-        int rc = scatter_grid<false>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<false>::kTileWords - 1) / ScatterCfg<false>::kTileWords, &grid);
-        if (rc) { cleanup(); return rc; }
+    int grid = 1;
+    int rc = scatter_grid<false>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<false>::kTileWords - 1) / ScatterCfg<false>::kTileWords, &grid);
+    if (rc) return rc;
+    {
+        Timed t(ctx, T_COUNT_SCATTER, 2);
+        bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, P.geo.cap);
+        if (ctx->p.k == 15) bucket_scatter_kernel<15, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
+        else bucket_scatter_kernel<0, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
+    }
+    if (P.two_level) {
         {
-            Timed t(ctx, T_COUNT_SCATTER, 2);
-            bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-            if (ctx->p.k == 15) bucket_scatter_kernel<15, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
-            else bucket_scatter_kernel<0, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
+            Timed t(ctx, T_COUNT_SPLIT, 2);
+            sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(P.ss, P.sg);
+            bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(P.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts);
         }
-        if (two_level) {
-            {
-                Timed t(ctx, T_COUNT_SPLIT, 2);
-                sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(ss, sg);
-                bucket_split_kernel<<<split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(entries, geo, ctx->d_bucket, sg, ss, entries2, ctx->counts);
-            }
-            Timed t(ctx, T_COUNT, 2);
-            sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(ss, sg);
-            sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(entries2, sg, ss, ctx->counts);
-        } else {
-            Timed t(ctx, T_COUNT, 1);
-            bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, ctx->counts);
-        }
+        Timed t(ctx, T_COUNT, 2);
+        sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(P.ss, P.sg);
+        sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(P.entries2, P.sg, P.ss, ctx->counts);
+    } else {
+        Timed t(ctx, T_COUNT, 1);
+        bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P.entries, P.geo, ctx->d_bucket, ctx->counts);
     }
     CK(cudaGetLastError());
-    cleanup();
     return PG_OK;
+}
+
+static int count_bucketed(pg_ctx* ctx, pg_batch* b)
+{
+    CountPlan P;
+    int rc = count_plan_init(ctx, b->n_words, P);
+    for (int64_t w0 = 0; !rc && w0 < b->n_words; w0 += P.seg_words) rc = count_segment(ctx, P, b, w0, std::min(b->n_words, w0 + P.seg_words));
+    count_plan_free(ctx, P);
+    return rc;
 }
 
 extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
@@ -1032,6 +1093,53 @@ extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
 // ---------------------------------------------------------------------------
 // whole path, host buffers in
 // ---------------------------------------------------------------------------
+// Sliced (dense k <= 15) path: the batch crosses PCIe in chunks on a second stream while the
+// compute stream packs chunk c and counts chunk c - 1 (a window of chunk c - 1 may end in the first
+// words of chunk c), so the count pass hides behind the copy.  Featurize needs the complete table
+// and starts when the last chunk is counted.
+static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
+{
+    pg_batch* b = nullptr;
+    int rc = alloc_batch(ctx, h, &b);
+    if (rc) return rc;
+    CountPlan P;
+    rc = count_plan_init(ctx, b->n_words, P);
+    if (rc) { pg_batch_free(ctx, b); return rc; }
+    cudaEvent_t ev = Timed::get(ctx);
+    auto bail = [&](int code) { // copies may still be in flight into the buffers freed here
+        cudaStreamSynchronize(ctx->copy_stream);
+        count_plan_free(ctx, P); pg_batch_free(ctx, b); ctx->pool.push_back(ev);
+        return code;
+    };
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    CKB(cudaEventRecord(ev, ctx->stream));             // allocations (stream-ordered) and the table clear come first
+    CKB(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+    const int64_t n_chunks = (b->n_words + P.seg_words - 1) / P.seg_words;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t w0 = c * P.seg_words, w1 = std::min(b->n_words, w0 + P.seg_words);
+        const size_t lo = (size_t)w0 * 32, hi = std::min<size_t>((size_t)w1 * 32, (size_t)b->n_bytes);
+        CKB(cudaMemcpyAsync(b->seq + lo, h->seq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (b->qual) CKB(cudaMemcpyAsync(b->qual + lo, h->qual + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CKB(cudaEventRecord(ev, ctx->copy_stream));    // a recorded event may be re-recorded: the wait below captured this record
+        CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));
+        rc = pack_range(ctx, b, w0, c + 1 == n_chunks ? b->n_words + 2 : w1);
+        if (!rc && c > 0) rc = count_segment(ctx, P, b, (c - 1) * P.seg_words, w0);
+        if (rc) return bail(rc);
+    }
+    rc = count_segment(ctx, P, b, (n_chunks - 1) * P.seg_words, b->n_words);
+    if (rc) return bail(rc);
+    CKB(cudaMemcpyAsync(b->read_off, h->read_off, ((size_t)h->n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CKB(cudaMemcpyAsync(b->read_flag, h->read_flag, (size_t)h->n_reads, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CKB(cudaEventRecord(ev, ctx->copy_stream));
+    CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));
+#undef CKB
+    count_plan_free(ctx, P);
+    ctx->pool.push_back(ev);
+    ctx->counted = true;
+    *out = b;
+    return PG_OK;
+}
+
 extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
 {
     if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
@@ -1039,9 +1147,15 @@ extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint
     int rc = pg_table_clear(ctx);
     if (rc) return rc;
     pg_batch* b = nullptr;
-    rc = pg_batch_upload(ctx, host, &b);
-    if (rc) return rc;
-    rc = pg_count(ctx, b);
+    if (use_buckets(ctx) && host && host->n_reads > 0 && host->n_bytes >= (1 << 20)) {
+        rc = check_host_batch(ctx, host);
+        if (!rc) rc = upload_and_count_pipelined(ctx, host, &b);
+        if (rc) return rc;
+    } else {
+        rc = pg_batch_upload(ctx, host, &b);
+        if (rc) return rc;
+        rc = pg_count(ctx, b);
+    }
     pg_features* f = nullptr;
     if (!rc) rc = pg_featurize(ctx, b, group_keep, n_groups, &f);
     if (!rc) rc = pg_normalize(ctx, f);

@@ -445,7 +445,9 @@ bucket_apply_count_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, 
     }
 }
 
-// sweep the partitioned entries slice by slice: gather (L2 hit), bin, reduce
+// sweep the partitioned entries slice by slice: gather (L2 hit), bin, reduce.
+// The ticket of the NEXT chunk is requested before the current chunk is processed and read when it
+// is done, so the round trip of the global atomic is hidden behind the chunk's own work.
 __global__ void __launch_bounds__(256)
 bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __restrict__ meta, BucketGeom geo,
                          BucketState* __restrict__ st, const FeatParams P)
@@ -453,12 +455,15 @@ bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __
     __shared__ ApplySmem A;
     apply_prologue(A, geo, st);
     const unsigned long long n_chunks = A.chunk_base[geo.n_buckets];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
+    __syncthreads();
     int b = 0;
     for (;;) {
-        if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
-        __syncthreads();
         const unsigned long long c = A.ticket;
-        __syncthreads();
+        unsigned long long next = 0ull;
+        __syncthreads(); // everyone has read A.ticket
+        if (threadIdx.x == 0) next = atomicAdd(&st->ticket, 1ull); // in flight while the chunk is processed
         if (c >= n_chunks) break;
         while (A.chunk_base[b + 1] <= c) ++b;
         const unsigned long long off = (unsigned long long)b * geo.cap + (c - A.chunk_base[b]) * kChunk; // multiple of 32
@@ -472,18 +477,27 @@ bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __
         for (int u = 0; u < kChunk / 256; ++u) {
             const uint32_t i = threadIdx.x + 256u * u;
             e[u] = i < n ? __ldcs(src + i) : kInvalidEntry;
-            row0[u] = i < n ? __ldg(row0_of + (i >> 5)) : 0;
+            row0[u] = i < n ? __ldg(row0_of + (i >> 5)) : 0; // one base row per warp-wide group of 32 entries
         }
 #pragma unroll
         for (int u = 0; u < kChunk / 256; ++u)
             cnt[u] = e[u] != kInvalidEntry ? __ldg(slice + ((e[u] >> 3) & geo.low_mask)) : 0u;
 #pragma unroll
         for (int u = 0; u < kChunk / 256; ++u) {
-            unsigned long long key = 0;
-            const uint32_t row = (uint32_t)row0[u] + (((e[u] >> 26) << 3) | (e[u] & 7u));
-            const bool live = abd_key(P, cnt[u], row, key); // cnt = 0 for padding
-            abd_reduce_warp(P, live, key);
+            // the 32 entries of a warp share row0: (delta, bin) identifies the tally inside the warp in 22 bits
+            const uint32_t delta = ((e[u] >> 26) << 3) | (e[u] & 7u);
+            uint32_t c32 = cnt[u] & kCountMask;
+            const bool live = cnt[u] != 0u && c32 < P.clamp; // absent k-mers are skipped (count_kmer.cpp:87); cnt = 0 for padding
+            const uint32_t key = (delta << 13) | (live ? abd_bin(P, c32) : 0u); // vector_size <= 8192
+            const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const uint32_t peers = __match_any_sync(live_mask, key);
+                if (lane == __ffs(peers) - 1)
+                    atomicAdd(P.abd + (int64_t)((uint32_t)row0[u] + delta) * P.vs + (key & 0x1FFFu), (uint32_t)__popc(peers));
+            }
         }
+        if (threadIdx.x == 0) A.ticket = next;
+        __syncthreads();
     }
 }
 
