@@ -154,6 +154,8 @@ class ClockSampler:
         self.index, self.proc, self.path = index, None, None
 
     def start(self):
+        if os.environ.get("PG_NO_CLOCKS") == "1":  # experiment switch: does the sampler perturb the run?
+            return
         try:
             self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
@@ -281,18 +283,36 @@ def main():
         if world > 1:
             dist.barrier()
 
+    debug = os.environ.get("PG_DEBUG_STEP") == "1"
+    debug_ev = [] if os.environ.get("PG_DEBUG_STEP") == "2" else None
+
     def step_device():
         """inputs resident in HBM -> normalised matrices in HBM"""
-        ctx.table_clear()
-        b = ctx.adopt(batch_data["reads"])
-        ctx.count(b)
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if debug:
+                ctx.synchronize()
+                marks.append((name, time.perf_counter()))
+            elif debug_ev is not None:  # no syncs: CUDA events on the ctx stream, read after the run
+                e = torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e.record()
+                debug_ev.append((name, e, time.perf_counter()))
+
+        ctx.table_clear(); mark("clear")
+        b = ctx.adopt(batch_data["reads"]); mark("adopt+pack")
+        ctx.count(b); mark("count")
         if world > 1:  # the one exchange step of the path: sum the dense count tables
             ctx.synchronize()
             dist.all_reduce(table_t)
             torch.cuda.synchronize()
-        f = ctx.featurize(b, keep)
-        f.normalize()
-        b.free()
+        f = ctx.featurize(b, keep); mark("featurize")
+        f.normalize(); mark("normalize")
+        b.free(); mark("free")
+        if debug:
+            free_b, total_b = torch.cuda.mem_get_info()
+            print("step:", " ".join(f"{n}={1e3 * (t - marks[i][1]):.1f}" for i, (n, t) in enumerate(marks[1:])), f"free={free_b / 2**30:.1f}GiB", file=sys.stderr, flush=True)
         return f
 
     for _ in range(args.warmup):
@@ -317,6 +337,16 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
+    if debug_ev:
+        timed = [x for x in debug_ev if x[2] >= t0]
+        prev_e, prev_t = ev0, t0
+        line = []
+        for name, e, t in timed:
+            line.append(f"{name}:dev={prev_e.elapsed_time(e):.1f}/host={1e3 * (t - prev_t):.1f}")
+            prev_e, prev_t = e, t
+            if name == "free":
+                print("step:", " ".join(line), file=sys.stderr, flush=True)
+                line = []
     clocks = sampler.stop() if rank == 0 else None
     stage_ms = {n: ctx.timing(w)[0] / args.steps for n, w in STAGE_SLOTS}
     stage_launches = {n: ctx.timing(w)[1] // args.steps for n, w in STAGE_SLOTS}

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpangaea_b200.so")
+LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(HERE, "libpangaea_b200.so")  # PG_LIB_PATH: A/B builds (tools/)
 
 PG_READ_CHANGE, PG_READ_NOFEAT = 1, 2
 PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH = 0, 1, 2

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -31,6 +33,23 @@ using namespace pg;
 // timing slots: one per kernel family (pg_timing_get `which`)
 enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_COUNT_SPLIT = 9, T_SLOTS = 10 };
 
+// grow-only device scratch kept by the ctx: the multi-GB partition buffers are allocated once, not once per step
+// (72 GB of cudaMallocAsync / cudaFreeAsync per step made the pool re-map memory: step times of 106 .. 380 ms)
+struct Workspace {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+// Block cache for allocations >= 1 MiB (packed stream, cloud maps, feature matrices).  Steps repeat the same sizes,
+// so after the first step every request is served from the free list without a driver call.  cudaMallocAsync was
+// measured to fall back to a fresh mapping now and then (100+ ms per GB, host and stream both stalled) when 10+ GB per
+// step went through the pool.  All work of a ctx is on one stream, so a freed block may be handed out again at once.
+struct BigCache {
+    std::unordered_map<void*, size_t> live;   // block -> capacity
+    std::multimap<size_t, void*> free_blocks; // capacity -> block
+    size_t free_bytes = 0;
+};
+
 struct pg_ctx {
     pg_params p;
     int td = 0;
@@ -49,9 +68,13 @@ struct pg_ctx {
     // pinned read-back scratch
     int64_t* h_pin = nullptr;
     int64_t* d_scalar = nullptr; // 8 x int64 device scalars
+    Workspace ws_entries, ws_entries2, ws_feat; // level-1 / level-2 entries of the count pass, entries of an unshared featurize pass
+    BigCache big;
+    Workspace ws_stash;                         // one cached shared-partition buffer (taken by a batch in pg_count, returned by pg_batch_free)
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
+    bool no_shared = false;      // PG_NO_SHARED=1: separate partitions for the count and featurize passes (A/B, tests)
     bool count_l2 = false;       // PG_COUNT_L2=1: apply the count entries with L2 atomics instead of the shared-memory sub-slices (A/B)
     int64_t count_seg_words = 1ll << 26; // segment of the count pass (2^31 windows: 13 GB of u32 + 6 GB of u16 entries); PG_SEG_WORDS overrides
     int64_t seg_words = 1ll << 26; // words per segment of the featurize pass: 2^31 windows -> 14 GB of u32 entries with the default
@@ -72,6 +95,19 @@ struct pg_batch {
     uint64_t* codes = nullptr;
     uint32_t *maskF = nullptr, *maskC = nullptr;
     int64_t n_groups = -1; // counted on device, lazily
+    // cloud structure derived from the read flags alone (group_stage_a): shared by pg_count and pg_featurize
+    bool grouped = false;
+    int64_t nofeat = 0;                        // reads with PG_READ_NOFEAT
+    int64_t* gstart = nullptr;                 // n_groups + 1 cloud starts (byte offsets)
+    unsigned long long* nofeat_len = nullptr;  // n_groups: bytes of NOFEAT reads per cloud
+    uint32_t* maskR = nullptr;                 // maskF without the NOFEAT reads (only when nofeat > 0)
+    uint32_t* wg = nullptr;                    // n_words: word -> cloud map (sliced path)
+    int64_t min_group_len = 0;
+    // entries of the shared partition: written by pg_count, reused by pg_featurize (bucket.cuh: kScatterShared)
+    struct Segment { int64_t w0, w1; uint32_t* entries; int32_t* meta; unsigned long long* fill; BucketGeom geo; };
+    std::vector<Segment> stash;
+    Workspace stash_ws;                        // backing store of all segments (borrowed from / returned to the ctx)
+    uint32_t* stash_lost = nullptr;            // device flag: an overflow path bypassed the entry buffer
 };
 
 struct pg_features {
@@ -132,12 +168,71 @@ static inline int grid_for(int64_t n, int threads, int cap)
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
 }
 
+// scratch of at least `bytes`; contents undefined.  Re-allocation waits for the stream (the old block may be in use).
+static cudaError_t ws_get(pg_ctx* ctx, Workspace& w, size_t bytes)
+{
+    if (w.bytes >= bytes && w.p) return cudaSuccess;
+    if (w.p) { cudaStreamSynchronize(ctx->stream); cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+    cudaError_t e = cudaMalloc(&w.p, std::max<size_t>(bytes, 256));
+    if (e == cudaSuccess) w.bytes = std::max<size_t>(bytes, 256);
+    else { w.p = nullptr; cudaGetLastError(); }
+    return e;
+}
+
+constexpr size_t kBigBlock = 1u << 20;          // smaller requests stay with cudaMallocAsync
+constexpr size_t kBigCacheLimit = 48ull << 30;  // idle bytes kept before the largest blocks are released
+
+static void big_trim(pg_ctx* ctx, size_t keep_bytes)
+{
+    if (ctx->big.free_bytes <= keep_bytes) return;
+    cudaStreamSynchronize(ctx->stream); // a cached block may still be read by queued work
+    while (ctx->big.free_bytes > keep_bytes && !ctx->big.free_blocks.empty()) {
+        auto it = std::prev(ctx->big.free_blocks.end());
+        cudaFree(it->second);
+        ctx->big.free_bytes -= it->first;
+        ctx->big.free_blocks.erase(it);
+    }
+}
+
+static cudaError_t big_alloc(pg_ctx* ctx, void** p, size_t bytes)
+{
+    bytes = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    auto it = ctx->big.free_blocks.lower_bound(bytes);
+    if (it != ctx->big.free_blocks.end() && it->first <= bytes + bytes / 4) {
+        *p = it->second;
+        ctx->big.live[*p] = it->first;
+        ctx->big.free_bytes -= it->first;
+        ctx->big.free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { // out of memory: give the idle blocks back and try once more
+        cudaGetLastError();
+        big_trim(ctx, 0);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) ctx->big.live[*p] = bytes;
+    else cudaGetLastError();
+    return e;
+}
+
 template <class T>
 static cudaError_t dmalloc(pg_ctx* ctx, T** p, size_t n)
 {
-    return cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (bytes >= kBigBlock) return big_alloc(ctx, (void**)p, bytes);
+    return cudaMallocAsync((void**)p, bytes, ctx->stream);
 }
-static void dfree(pg_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+static void dfree(pg_ctx* ctx, void* p)
+{
+    if (!p) return;
+    auto it = ctx->big.live.find(p);
+    if (it == ctx->big.live.end()) { cudaFreeAsync(p, ctx->stream); return; }
+    ctx->big.free_blocks.insert({ it->second, p });
+    ctx->big.free_bytes += it->second;
+    ctx->big.live.erase(it);
+    big_trim(ctx, kBigCacheLimit);
+}
 
 // ---------------------------------------------------------------------------
 // TNF column table (count_tnf.cpp:54-76,138-164): column = rank of the canonical code
@@ -243,6 +338,11 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
         CKC(cudaDeviceGetDefaultMemPool(&pool, p->device));
         uint64_t keep = ~0ull;
         CKC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // reuse by stream order only: with the opportunistic policies the block a request gets depends on how far the host
+        // runs ahead of the GPU, and an unlucky choice ends in a fresh mapping (100+ ms per GB) in the middle of a step
+        int off = 0;
+        CKC(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowOpportunistic, &off));
+        CKC(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
     }
     CKC(cudaMalloc((void**)&ctx->d_lut, lut.size() * sizeof(uint16_t)));
     CKC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -254,6 +354,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     { const char* e = getenv("PG_FORCE_DIRECT"); ctx->force_direct = e && e[0] == '1'; }
     { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = ctx->count_seg_words = atoll(e) / 512 * 512; }
     { const char* e = getenv("PG_COUNT_L2"); ctx->count_l2 = e && e[0] == '1'; }
+    { const char* e = getenv("PG_NO_SHARED"); ctx->no_shared = e && e[0] == '1'; }
     { const char* e = getenv("PG_FEAT_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
@@ -266,10 +367,12 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     }
     CKC(cudaFuncSetAttribute(featurize_kernel<kDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CKC(cudaFuncSetAttribute(featurize_kernel<kHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
-    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
-    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
-    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, kScatterCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, kScatterCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<false>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, kScatterFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, kScatterFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
+    CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
     CKC(cudaFuncSetAttribute(sub_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubWords * 4 + 16));
     CKC(cudaFuncSetAttribute(tnf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -288,6 +391,8 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
+    for (auto& kv : ctx->big.free_blocks) cudaFree(kv.second); // (live blocks belong to batches / feature sets still around)
+    cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p); cudaFree(ctx->ws_stash.p);
     cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -452,12 +557,26 @@ extern "C" int pg_batch_adopt(pg_ctx* ctx, const pg_reads* d, pg_batch** out)
     return PG_OK;
 }
 
+static void free_stash(pg_ctx* ctx, pg_batch* b)
+{
+    b->stash.clear();
+    if (b->stash_ws.p) { // back to the ctx (later use is ordered on the same stream), or released when the ctx already holds one
+        if (!ctx->ws_stash.p) ctx->ws_stash = b->stash_ws;
+        else { cudaStreamSynchronize(ctx->stream); cudaFree(b->stash_ws.p); }
+        b->stash_ws = Workspace();
+    }
+    dfree(ctx, b->stash_lost);
+    b->stash_lost = nullptr;
+}
+
 extern "C" void pg_batch_free(pg_ctx* ctx, pg_batch* b)
 {
     if (!b || !ctx) return;
     cudaSetDevice(ctx->p.device);
     if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); dfree(ctx, b->read_off); dfree(ctx, b->read_flag); }
     dfree(ctx, b->codes); dfree(ctx, b->maskF); dfree(ctx, b->maskC);
+    dfree(ctx, b->gstart); dfree(ctx, b->nofeat_len); dfree(ctx, b->maskR); dfree(ctx, b->wg);
+    free_stash(ctx, b);
     delete b;
 }
 
@@ -514,21 +633,30 @@ static BucketGeom bucket_geom(const pg_ctx* ctx, int64_t seg_words)
 }
 
 // grid of a scatter launch: every resident CTA walks tiles with a grid stride
-template <bool FEAT>
-static int scatter_grid(pg_ctx* ctx, int k, int64_t n_tiles, int* grid_out)
+template <int MODE>
+static int scatter_launch(pg_ctx* ctx, const ScatterParams& Q, const FeatParams& P)
 {
+    constexpr bool FEAT = MODE != kScatterCount;
+    const int64_t n_tiles = (Q.w1 - Q.w0 + ScatterCfg<FEAT>::kTileWords - 1) / ScatterCfg<FEAT>::kTileWords;
     int occ = 1;
-    if (k == 15) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<15, FEAT>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<0, FEAT>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
+    if (Q.k == 15) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<15, MODE>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_scatter_kernel<0, MODE>, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>)));
     if (occ < 1) return fail(ctx, PG_ERR_CUDA, "scatter kernel does not fit on this device");
-    *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * occ));
+    bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, Q.geo.cap);
+    if (Q.k == 15) bucket_scatter_kernel<15, MODE><<<grid, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>), ctx->stream>>>(Q, P);
+    else bucket_scatter_kernel<0, MODE><<<grid, ScatterCfg<FEAT>::kThreads, sizeof(ScatterSmem<FEAT>), ctx->stream>>>(Q, P);
+    CK(cudaGetLastError());
     return PG_OK;
 }
+
+static int group_stage_a(pg_ctx* ctx, pg_batch* b, bool want_wg, bool packed = true);
 
 // buffers and geometry of the sliced count pass, set up once per batch; segments are then
 // counted one by one (pg_extract_features interleaves them with the upload)
 struct CountPlan {
     bool two_level = false;
+    bool shared = false;    // the level-1 entries also serve the featurize pass: one buffer per segment, kept in the batch
     int64_t seg_words = 0;
     BucketGeom geo = {};
     SubGeom sg = {};
@@ -540,23 +668,86 @@ struct CountPlan {
 
 static void count_plan_free(pg_ctx* ctx, CountPlan& P)
 {
-    dfree(ctx, P.entries); dfree(ctx, P.entries2); dfree(ctx, P.ss.cursors); dfree(ctx, P.ss.limits); dfree(ctx, P.ss.item_base);
+    dfree(ctx, P.ss.cursors); dfree(ctx, P.ss.limits); dfree(ctx, P.ss.item_base); // the entry buffers belong to the ctx / the batch
     P = CountPlan();
 }
 
-static int count_plan_init(pg_ctx* ctx, int64_t n_words, CountPlan& P)
+// memory cudaMallocAsync can still hand out: free device memory + what the pool holds but does not use
+static size_t available_bytes(pg_ctx* ctx)
 {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->p.device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += (size_t)(reserved - used);
+    return free_b;
+}
+
+static BucketGeom padded_geom(BucketGeom geo) // feature-format runs are padded to 32 entries
+{
+    geo.cap = (unsigned long long)((double)geo.cap * 1.08 / 32.0 + 1.0) * 32ull;
+    return geo;
+}
+
+// One partition for both passes (bucket.cuh: kScatterShared) when the batch allows it: no quality filter (feature
+// windows must be a subset of the counted ones), every cloud >= 64 bytes, and room to keep the entries until
+// pg_featurize.  Otherwise each pass partitions for itself.
+static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed = true)
+{
+    const int64_t n_words = b->n_words;
     P.two_level = !ctx->count_l2;
     P.seg_words = std::max<int64_t>(1, std::min<int64_t>(n_words, P.two_level ? ctx->count_seg_words : ctx->seg_words));
     P.geo = bucket_geom(ctx, P.seg_words);
-    cudaError_t e = dmalloc(ctx, &P.entries, (size_t)P.geo.cap * P.geo.n_buckets);
+    P.shared = false;
+    if (P.two_level && !ctx->no_shared && !ctx->p.min_qual_char && b->stash.empty() && b->read_flag && b->read_off && n_words > 0) {
+        int rc = group_stage_a(ctx, b, true, packed);
+        if (rc) return rc;
+        const BucketGeom pg = padded_geom(P.geo);
+        const size_t n_seg = (size_t)((n_words + P.seg_words - 1) / P.seg_words);
+        const size_t per_seg = (size_t)pg.cap * pg.n_buckets * 4 + (size_t)pg.cap * pg.n_buckets / 32 * 4 + kMaxBuckets * sizeof(unsigned long long);
+        const size_t need = n_seg * per_seg;
+        if (b->min_group_len >= 64 && (packed || !b->nofeat) &&
+            (need <= ctx->ws_stash.bytes || (double)need <= 0.7 * (double)(available_bytes(ctx) + ctx->ws_stash.bytes))) {
+            b->stash_ws = ctx->ws_stash; // borrow the cached buffer (grown if too small)
+            ctx->ws_stash = Workspace();
+            if (ws_get(ctx, b->stash_ws, need) == cudaSuccess) {
+                P.shared = true;
+                P.geo = pg;
+                uint8_t* base = (uint8_t*)b->stash_ws.p;
+                const size_t E = (size_t)pg.cap * pg.n_buckets;
+                for (size_t i = 0; i < n_seg; ++i) {
+                    pg_batch::Segment sgm;
+                    sgm.w0 = (int64_t)i * P.seg_words; sgm.w1 = std::min<int64_t>(n_words, sgm.w0 + P.seg_words);
+                    sgm.entries = (uint32_t*)(base + i * E * 4);
+                    sgm.meta = (int32_t*)(base + n_seg * E * 4 + i * (E / 32) * 4);
+                    sgm.fill = (unsigned long long*)(base + n_seg * E * 4 + n_seg * (E / 32) * 4 + i * kMaxBuckets * sizeof(unsigned long long));
+                    sgm.geo = pg;
+                    b->stash.push_back(sgm);
+                }
+            } else {
+                free_stash(ctx, b);
+            }
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (P.shared) {
+        e = dmalloc(ctx, &b->stash_lost, 1);
+        if (e == cudaSuccess) e = cudaMemsetAsync(b->stash_lost, 0, sizeof(uint32_t), ctx->stream);
+    } else {
+        e = ws_get(ctx, ctx->ws_entries, (size_t)P.geo.cap * P.geo.n_buckets * 4);
+        P.entries = (uint32_t*)ctx->ws_entries.p;
+    }
     if (e == cudaSuccess && P.two_level) {
         P.sg.n_sub = P.geo.n_buckets * kSubFan;
         const double mean = (double)P.seg_words * 32.0 / P.sg.n_sub;
         // runs are padded to 8 entries: + 3.5 entries per run of 64 x (valid fraction) on average
         P.sg.cap = (uint32_t)std::min<double>(4.0e9, std::max(64.0, std::ceil(mean * 1.08 * ctx->region_slack / 8.0) * 8.0));
         P.sg.chunk = (uint32_t)std::max<double>(131072.0, std::ceil(2.0 * mean / 8.0) * 8.0);
-        e = dmalloc(ctx, &P.entries2, (size_t)P.sg.cap * P.sg.n_sub);
+        e = ws_get(ctx, ctx->ws_entries2, (size_t)P.sg.cap * P.sg.n_sub * 2);
+        P.entries2 = (uint16_t*)ctx->ws_entries2.p;
         if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.cursors, (size_t)P.sg.n_sub);
         if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.limits, (size_t)P.sg.n_sub);
         if (e == cudaSuccess) e = dmalloc(ctx, &P.ss.item_base, (size_t)P.sg.n_sub + 1);
@@ -564,39 +755,47 @@ static int count_plan_init(pg_ctx* ctx, int64_t n_words, CountPlan& P)
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bucket_split_kernel, kSplitThreads, sizeof(SplitSmem));
         P.split_grid = ctx->sm_count * std::max(occ, 1);
     }
-    if (e != cudaSuccess) { count_plan_free(ctx, P); return fail(ctx, PG_ERR_CUDA, std::string("count pass: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { count_plan_free(ctx, P); free_stash(ctx, b); return fail(ctx, PG_ERR_CUDA, std::string("count pass: ") + cudaGetErrorString(e)); }
     return PG_OK;
 }
 
 // count the windows that start in words [w0, w1) (w1 - w0 <= plan.seg_words); words w1, w1 + 1 must be packed too
 static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int64_t w1)
 {
-    ScatterParams Q;
+    ScatterParams Q = {};
     Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = P.geo; Q.st = ctx->d_bucket;
-    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts;
+    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts; Q.lost = nullptr;
     Q.w0 = w0; Q.w1 = w1;
-    const FeatParams none = {};
-    int grid = 1;
-    int rc = scatter_grid<false>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<false>::kTileWords - 1) / ScatterCfg<false>::kTileWords, &grid);
-    if (rc) return rc;
-    {
+    FeatParams F = {};
+    int rc = PG_OK;
+    if (P.shared) {
+        const size_t si = (size_t)(w0 / P.seg_words);
+        if (si >= b->stash.size() || b->stash[si].w0 != w0 || b->stash[si].w1 != w1) return fail(ctx, PG_ERR_STATE, "count pass: segment does not match the shared partition plan");
+        const pg_batch::Segment& sgm = b->stash[si];
+        Q.entries = sgm.entries; Q.meta = sgm.meta; Q.lost = b->stash_lost;
+        F.maskF = b->maskR ? b->maskR : b->maskF; F.wg = b->wg; F.gstart = b->gstart; F.n_groups = b->n_groups;
+        {
+            Timed t(ctx, T_COUNT_SCATTER, 3);
+            rc = scatter_launch<kScatterShared>(ctx, Q, F);
+            if (!rc) bucket_save_fill_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, P.geo, sgm.fill);
+        }
+    } else {
         Timed t(ctx, T_COUNT_SCATTER, 2);
-        bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, P.geo.cap);
-        if (ctx->p.k == 15) bucket_scatter_kernel<15, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
-        else bucket_scatter_kernel<0, false><<<grid, ScatterCfg<false>::kThreads, sizeof(ScatterSmem<false>), ctx->stream>>>(Q, none);
+        rc = scatter_launch<kScatterCount>(ctx, Q, F);
     }
+    if (rc) return rc;
     if (P.two_level) {
         {
             Timed t(ctx, T_COUNT_SPLIT, 2);
             sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(P.ss, P.sg);
-            bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(P.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts);
+            bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts);
         }
         Timed t(ctx, T_COUNT, 2);
         sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(P.ss, P.sg);
         sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(P.entries2, P.sg, P.ss, ctx->counts);
     } else {
         Timed t(ctx, T_COUNT, 1);
-        bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P.entries, P.geo, ctx->d_bucket, ctx->counts);
+        bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, ctx->counts);
     }
     CK(cudaGetLastError());
     return PG_OK;
@@ -605,7 +804,8 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
 static int count_bucketed(pg_ctx* ctx, pg_batch* b)
 {
     CountPlan P;
-    int rc = count_plan_init(ctx, b->n_words, P);
+    free_stash(ctx, b); // counting a batch again: its old entries are stale
+    int rc = count_plan_init(ctx, b, P);
     for (int64_t w0 = 0; !rc && w0 < b->n_words; w0 += P.seg_words) rc = count_segment(ctx, P, b, w0, std::min(b->n_words, w0 + P.seg_words));
     count_plan_free(ctx, P);
     return rc;
@@ -759,6 +959,70 @@ static int scan_flags(pg_ctx* ctx, const uint8_t* d_flags, int64_t n, uint32_t b
 
 extern "C" int64_t pg_batch_n_groups(const pg_batch* b) { return b ? b->n_groups : -1; }
 
+// smallest cloud of the batch, in bytes (0 when some cloud is empty)
+__global__ void min_group_len_kernel(const int64_t* __restrict__ gstart, int64_t n_groups, unsigned long long* __restrict__ out)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long len = ~0ull;
+    if (g < n_groups) len = (unsigned long long)(gstart[g + 1] - gstart[g]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) len = min(len, __shfl_xor_sync(0xffffffffu, len, d));
+    if ((threadIdx.x & 31) == 0 && len != ~0ull) atomicMin(out, len);
+}
+
+// Cloud structure that follows from the read flags alone: NOFEAT reads masked out of the feature mask,
+// cloud starts, word -> cloud map.  Kept in the batch: pg_count (shared partition) and pg_featurize both use it.
+// packed = false: the stream is not packed yet (pipelined upload) - the NOFEAT mask is left for a later call
+static int group_stage_a(pg_ctx* ctx, pg_batch* b, bool want_wg, bool packed)
+{
+    if (b->grouped && (!want_wg || b->wg || !b->n_words) && (!b->nofeat || b->maskR || !packed)) return PG_OK;
+    int32_t* tile_off = nullptr;
+    int64_t changes = 0;
+    int rc = PG_OK;
+    Timed t(ctx, T_GROUP, 8);
+    if (!b->grouped) {
+        // PG_READ_NOFEAT reads are rare; when present their bases are masked out of a working copy of maskF
+        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_NOFEAT, &tile_off, &b->nofeat);
+        if (rc) return rc;
+        dfree(ctx, tile_off);
+        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_CHANGE, &tile_off, &changes);
+        if (rc) return rc;
+        b->n_groups = changes + 1;
+        const int64_t n_groups = b->n_groups;
+        if (n_groups > 0x7FFFFFFFll) { dfree(ctx, tile_off); return fail(ctx, PG_ERR_INVALID, "more than 2^31 clouds in one batch"); }
+        CK(dmalloc(ctx, &b->gstart, (size_t)n_groups + 1));
+        CK(dmalloc(ctx, &b->nofeat_len, (size_t)n_groups));
+        CK(cudaMemsetAsync(b->nofeat_len, 0, (size_t)n_groups * sizeof(unsigned long long), ctx->stream));
+        if (b->n_reads == 0) {
+            CK(cudaMemsetAsync(b->gstart, 0, 2 * sizeof(int64_t), ctx->stream));
+        } else {
+            const int64_t n_tiles = std::max<int64_t>(1, (b->n_reads + kScanTile - 1) / kScanTile);
+            group_starts_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(b->read_flag, b->read_off, b->n_reads, tile_off, n_groups, b->gstart, b->nofeat_len);
+        }
+        dfree(ctx, tile_off);
+        CK(cudaMemsetAsync(ctx->d_scalar, 0xFF, sizeof(int64_t), ctx->stream));
+        min_group_len_kernel<<<(int)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(b->gstart, n_groups, (unsigned long long*)ctx->d_scalar);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        b->min_group_len = ctx->h_pin[0] < 0 ? 0 : ctx->h_pin[0];
+        b->grouped = true;
+    }
+    if (b->nofeat && !b->maskR && packed) {
+        CK(dmalloc(ctx, &b->maskR, (size_t)b->n_words + 2));
+        CK(cudaMemcpyAsync(b->maskR, b->maskF, ((size_t)b->n_words + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, b->maskR);
+        CK(cudaGetLastError());
+    }
+    if (want_wg && !b->wg && b->n_words) { // word -> cloud map of the streaming kernels
+        CK(dmalloc(ctx, &b->wg, (size_t)b->n_words));
+        word_groups_kernel<false><<<grid_for(b->n_groups * 32, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg);
+        word_groups_kernel<true><<<(int)std::min<int64_t>(b->n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg);
+        CK(cudaGetLastError());
+    }
+    return PG_OK;
+}
+
 extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
 {
     if (!ctx || !b || !out || n_groups < 1 || !group_keep) return fail(ctx, PG_ERR_INVALID, "pg_featurize: bad argument");
@@ -767,19 +1031,16 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     if (n_groups > 0x7FFFFFFFll) return fail(ctx, PG_ERR_INVALID, "more than 2^31 clouds in one batch");
     CK(cudaSetDevice(ctx->p.device));
 
-    int64_t* gstart = nullptr;
-    uint32_t *maskR = nullptr, *wg = nullptr, *feat_entries = nullptr;
-    unsigned long long* nofeat_len = nullptr;
     uint8_t *d_keep = nullptr, *emit = nullptr;
-    int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr, *row_lb = nullptr, *feat_meta = nullptr;
-    const bool sliced = use_buckets(ctx);
-    int64_t changes = 0, nofeat = 0, rows = 0;
+    int32_t *row_of_group = nullptr, *group_of_row_full = nullptr, *tile_off = nullptr, *row_lb = nullptr;
+    int64_t rows = 0;
     int rc = PG_OK;
     pg_features* f = nullptr;
+    const bool sliced = use_buckets(ctx);
     auto cleanup = [&]() {
-        dfree(ctx, gstart); dfree(ctx, nofeat_len); dfree(ctx, d_keep); dfree(ctx, emit);
-        dfree(ctx, row_of_group); dfree(ctx, group_of_row_full); dfree(ctx, maskR); dfree(ctx, feat_entries);
-        dfree(ctx, wg); dfree(ctx, row_lb); dfree(ctx, feat_meta);
+        dfree(ctx, d_keep); dfree(ctx, emit);
+        dfree(ctx, row_of_group); dfree(ctx, group_of_row_full);
+        dfree(ctx, row_lb);
     };
 #define CKF(call)                                                                                        \
     do {                                                                                                 \
@@ -792,44 +1053,21 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     } while (0)
 
     // ---- grouping --------------------------------------------------------
+    rc = group_stage_a(ctx, b, sliced);
+    if (rc) return rc;
+    if (b->n_groups != n_groups)
+        return fail(ctx, PG_ERR_INVALID, "pg_featurize: n_groups (" + std::to_string(n_groups) + ") != 1 + change flags (" + std::to_string(b->n_groups) + ")");
+    int64_t* const gstart = b->gstart;
+    uint32_t* const wg = b->wg;
     {
-        Timed t(ctx, T_GROUP, 11); // 3 scans x 2 kernels + starts + emit + rows + word -> cloud map (2)
-        CKF(dmalloc(ctx, &gstart, (size_t)n_groups + 1));
-        CKF(dmalloc(ctx, &nofeat_len, (size_t)n_groups));
+        Timed t(ctx, T_GROUP, 4); // emit + scan x 2 + rows
         CKF(dmalloc(ctx, &d_keep, (size_t)n_groups));
         CKF(dmalloc(ctx, &emit, (size_t)n_groups));
         CKF(dmalloc(ctx, &row_of_group, (size_t)n_groups));
         CKF(dmalloc(ctx, &group_of_row_full, (size_t)n_groups));
         CKF(dmalloc(ctx, &row_lb, (size_t)n_groups));
-        CKF(cudaMemsetAsync(nofeat_len, 0, (size_t)n_groups * sizeof(unsigned long long), ctx->stream));
         CKF(cudaMemcpyAsync(d_keep, group_keep, (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
-        // PG_READ_NOFEAT reads are rare; when present their bases are masked out of a working copy of maskF
-        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_NOFEAT, &tile_off, &nofeat);
-        if (rc) { cleanup(); return rc; }
-        dfree(ctx, tile_off);
-        if (nofeat) {
-            CKF(dmalloc(ctx, &maskR, (size_t)b->n_words + 2));
-            CKF(cudaMemcpyAsync(maskR, b->maskF, ((size_t)b->n_words + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            clear_mask_ranges_kernel<<<grid_for(b->n_reads, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->read_off, b->read_flag, b->n_reads, maskR);
-        }
-
-        rc = scan_flags(ctx, b->read_flag, b->n_reads, PG_READ_CHANGE, &tile_off, &changes);
-        if (rc) { cleanup(); return rc; }
-        b->n_groups = changes + 1;
-        if (b->n_groups != n_groups) {
-            dfree(ctx, tile_off); cleanup();
-            return fail(ctx, PG_ERR_INVALID, "pg_featurize: n_groups (" + std::to_string(n_groups) + ") != 1 + change flags (" + std::to_string(changes + 1) + ")");
-        }
-        {
-            const int64_t n_tiles = std::max<int64_t>(1, (b->n_reads + kScanTile - 1) / kScanTile);
-            if (b->n_reads == 0) {
-                CKF(cudaMemsetAsync(gstart, 0, 2 * sizeof(int64_t), ctx->stream));
-            } else {
-                group_starts_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(b->read_flag, b->read_off, b->n_reads, tile_off, n_groups, gstart, nofeat_len);
-            }
-        }
-        dfree(ctx, tile_off);
-        group_emit_kernel<<<(int)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(gstart, nofeat_len, d_keep, n_groups, ctx->p.min_length, emit);
+        group_emit_kernel<<<(int)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(gstart, b->nofeat_len, d_keep, n_groups, ctx->p.min_length, emit);
         CKF(cudaGetLastError());
         rc = scan_flags(ctx, emit, n_groups, 1u, &tile_off, &rows);
         if (rc) { cleanup(); return rc; }
@@ -838,11 +1076,6 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
             row_assign_kernel<<<(int)n_tiles, kScanThreads, 0, ctx->stream>>>(emit, n_groups, tile_off, row_of_group, group_of_row_full, row_lb);
         }
         dfree(ctx, tile_off);
-        if (sliced && b->n_words) { // word -> cloud map of the streaming kernels
-            CKF(dmalloc(ctx, &wg, (size_t)b->n_words));
-            word_groups_kernel<false><<<grid_for(n_groups * 32, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(gstart, n_groups, b->n_bytes, wg);
-            word_groups_kernel<true><<<(int)std::min<int64_t>(n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(gstart, n_groups, b->n_bytes, wg);
-        }
         CKF(cudaGetLastError());
     }
 
@@ -862,7 +1095,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     // ---- the pass over the bases -------------------------------------------
     if (rows && b->n_words) {
         FeatParams P;
-        P.codes = b->codes; P.maskF = maskR ? maskR : b->maskF; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
+        P.codes = b->codes; P.maskF = b->maskR ? b->maskR : b->maskF; P.n_words = b->n_words; P.n_bytes = b->n_bytes;
         P.gstart = gstart; P.n_groups = n_groups; P.row_of_group = row_of_group; P.wg = wg; P.row_lb = row_lb;
         P.tnf_k = ctx->p.tnf_k; P.vs = f->vs; P.td = f->td;
         P.ws = (uint32_t)ctx->p.window_size;
@@ -888,28 +1121,43 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 if (P.tnf_k == 4) tnf_kernel<4><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
                 else tnf_kernel<0><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
             }
-            const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
-            BucketGeom geo = bucket_geom(ctx, seg_words);
-            geo.cap = (unsigned long long)((double)geo.cap * 1.08 / 32.0 + 1.0) * 32ull; // runs are padded to 32 entries
-            CKF(dmalloc(ctx, &feat_entries, (size_t)geo.cap * geo.n_buckets));
-            CKF(dmalloc(ctx, &feat_meta, (size_t)geo.cap * geo.n_buckets / 32));
-            ScatterParams Q;
-            Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
-            Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts;
-            for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
-                const int64_t w1 = std::min(b->n_words, w0 + seg_words);
-                Q.w0 = w0; Q.w1 = w1;
-                int grid = 1;
-                rc = scatter_grid<true>(ctx, ctx->p.k, (w1 - w0 + ScatterCfg<true>::kTileWords - 1) / ScatterCfg<true>::kTileWords, &grid);
-                if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
-                {
-                    Timed t(ctx, T_FEAT_SCATTER, 2);
-                    bucket_reset_kernel<<<1, kMaxBuckets, 0, ctx->stream>>>(ctx->d_bucket, geo.cap);
-                    if (ctx->p.k == 15) bucket_scatter_kernel<15, true><<<grid, ScatterCfg<true>::kThreads, sizeof(ScatterSmem<true>), ctx->stream>>>(Q, P);
-                    else bucket_scatter_kernel<0, true><<<grid, ScatterCfg<true>::kThreads, sizeof(ScatterSmem<true>), ctx->stream>>>(Q, P);
+            // entries kept by pg_count (shared partition)?  usable unless an overflow path bypassed the buffer
+            bool reuse = !b->stash.empty() && b->stash_lost;
+            if (reuse) {
+                CKF(cudaMemcpyAsync(ctx->h_pin, b->stash_lost, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CKF(cudaStreamSynchronize(ctx->stream));
+                uint32_t lost = 0;
+                memcpy(&lost, ctx->h_pin, sizeof(lost));
+                int64_t covered = 0;
+                for (auto& sgm : b->stash) covered += sgm.w1 - sgm.w0;
+                reuse = !lost && covered == b->n_words;
+            }
+            if (reuse) {
+                for (auto& sgm : b->stash) {
+                    Timed t(ctx, T_FEAT, 2);
+                    bucket_reset_ticket_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_bucket);
+                    bucket_apply_feat_kernel<true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(sgm.entries, sgm.meta, sgm.geo, ctx->d_bucket, sgm.fill, P);
                 }
-                Timed t(ctx, T_FEAT, 1);
-                bucket_apply_feat_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, feat_meta, geo, ctx->d_bucket, P);
+            } else {
+                const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
+                const BucketGeom geo = padded_geom(bucket_geom(ctx, seg_words));
+                const size_t E = (size_t)geo.cap * geo.n_buckets;
+                CKF(ws_get(ctx, ctx->ws_feat, E * 4 + E / 32 * 4));
+                uint32_t* const feat_entries = (uint32_t*)ctx->ws_feat.p;
+                int32_t* const feat_meta = (int32_t*)((uint8_t*)ctx->ws_feat.p + E * 4);
+                ScatterParams Q = {};
+                Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
+                Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts; Q.lost = nullptr;
+                for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
+                    Q.w0 = w0; Q.w1 = std::min(b->n_words, w0 + seg_words);
+                    {
+                        Timed t(ctx, T_FEAT_SCATTER, 2);
+                        rc = scatter_launch<kScatterFeat>(ctx, Q, P);
+                    }
+                    if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
+                    Timed t(ctx, T_FEAT, 1);
+                    bucket_apply_feat_kernel<false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, feat_meta, geo, ctx->d_bucket, nullptr, P);
+                }
             }
             CKF(cudaGetLastError());
             cleanup();
@@ -946,7 +1194,7 @@ static void features_release(pg_features* f, pg_ctx* ctx = nullptr)
     void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
     for (void* p : bufs) {
         if (!p) continue;
-        if (ctx) cudaFreeAsync(p, ctx->stream); else cudaFree(p);
+        if (ctx) dfree(ctx, p); else cudaFree(p);
     }
     delete f;
 }
@@ -1069,6 +1317,11 @@ extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
     if (which >= 2 && !f->normalized) { fail(ctx, PG_ERR_STATE, "call pg_normalize first"); return nullptr; }
     cudaSetDevice(ctx->p.device);
     cudaStreamSynchronize(ctx->stream); // the consumer runs on its own stream
+    {   // the consumer's deleter may run on any thread, after the ctx is gone: take the buffers out of the ctx's block
+        // cache - from here on they are plain cudaMalloc blocks, released with cudaFree / cudaFreeAsync
+        void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
+        for (void* p : bufs) if (p) ctx->big.live.erase(p);
+    }
     DlHolder* h = new DlHolder();
     h->f = f;
     ++f->refs;
@@ -1103,38 +1356,50 @@ static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch**
     int rc = alloc_batch(ctx, h, &b);
     if (rc) return rc;
     CountPlan P;
-    rc = count_plan_init(ctx, b->n_words, P);
-    if (rc) { pg_batch_free(ctx, b); return rc; }
-    cudaEvent_t ev = Timed::get(ctx);
+    cudaEvent_t ev = Timed::get(ctx), ev_meta = Timed::get(ctx);
     auto bail = [&](int code) { // copies may still be in flight into the buffers freed here
         cudaStreamSynchronize(ctx->copy_stream);
-        count_plan_free(ctx, P); pg_batch_free(ctx, b); ctx->pool.push_back(ev);
+        count_plan_free(ctx, P); pg_batch_free(ctx, b); ctx->pool.push_back(ev); ctx->pool.push_back(ev_meta);
         return code;
     };
 #define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
     CKB(cudaEventRecord(ev, ctx->stream));             // allocations (stream-ordered) and the table clear come first
     CKB(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-    const int64_t n_chunks = (b->n_words + P.seg_words - 1) / P.seg_words;
-    for (int64_t c = 0; c < n_chunks; ++c) {
-        const int64_t w0 = c * P.seg_words, w1 = std::min(b->n_words, w0 + P.seg_words);
-        const size_t lo = (size_t)w0 * 32, hi = std::min<size_t>((size_t)w1 * 32, (size_t)b->n_bytes);
-        CKB(cudaMemcpyAsync(b->seq + lo, h->seq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (b->qual) CKB(cudaMemcpyAsync(b->qual + lo, h->qual + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CKB(cudaEventRecord(ev, ctx->copy_stream));    // a recorded event may be re-recorded: the wait below captured this record
-        CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));
-        rc = pack_range(ctx, b, w0, c + 1 == n_chunks ? b->n_words + 2 : w1);
-        if (!rc && c > 0) rc = count_segment(ctx, P, b, (c - 1) * P.seg_words, w0);
-        if (rc) return bail(rc);
-    }
-    rc = count_segment(ctx, P, b, (n_chunks - 1) * P.seg_words, b->n_words);
-    if (rc) return bail(rc);
+    // the read offsets / flags go first: the cloud structure (shared partition) is derived from them while chunk 0 is in flight
     CKB(cudaMemcpyAsync(b->read_off, h->read_off, ((size_t)h->n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
     CKB(cudaMemcpyAsync(b->read_flag, h->read_flag, (size_t)h->n_reads, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CKB(cudaEventRecord(ev, ctx->copy_stream));
-    CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    CKB(cudaEventRecord(ev_meta, ctx->copy_stream));
+    const int64_t seg = std::max<int64_t>(1, std::min<int64_t>(b->n_words, ctx->count_l2 ? ctx->seg_words : ctx->count_seg_words));
+    const int64_t n_chunks = (b->n_words + seg - 1) / seg;
+    auto copy_chunk = [&](int64_t c) -> cudaError_t {
+        const int64_t w0 = c * seg, w1 = std::min(b->n_words, w0 + seg);
+        const size_t lo = (size_t)w0 * 32, hi = std::min<size_t>((size_t)w1 * 32, (size_t)b->n_bytes);
+        cudaError_t e = cudaMemcpyAsync(b->seq + lo, h->seq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess && b->qual) e = cudaMemcpyAsync(b->qual + lo, h->qual + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream); // re-recording is fine: the wait below captured the previous record
+        return e;
+    };
+    CKB(copy_chunk(0));
+    CKB(cudaStreamWaitEvent(ctx->stream, ev_meta, 0));
+    CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));      // (chunk 0's record; captured now, before the event is re-recorded)
+    rc = count_plan_init(ctx, b, P, false);            // derives the cloud structure (host waits for the flags only)
+    if (rc) return bail(rc);
+    if (P.seg_words != seg) return bail(fail(ctx, PG_ERR_STATE, "pipelined upload: segment size mismatch"));
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t w0 = c * seg, w1 = std::min(b->n_words, w0 + seg);
+        if (c > 0) {
+            CKB(copy_chunk(c));
+            CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));
+        }
+        rc = pack_range(ctx, b, w0, c + 1 == n_chunks ? b->n_words + 2 : w1);
+        if (!rc && c > 0) rc = count_segment(ctx, P, b, (c - 1) * seg, w0);
+        if (rc) return bail(rc);
+    }
+    rc = count_segment(ctx, P, b, (n_chunks - 1) * seg, b->n_words);
+    if (rc) return bail(rc);
 #undef CKB
     count_plan_free(ctx, P);
-    ctx->pool.push_back(ev);
+    ctx->pool.push_back(ev); ctx->pool.push_back(ev_meta);
     ctx->counted = true;
     *out = b;
     return PG_OK;

@@ -40,11 +40,14 @@ namespace pg {
 
 constexpr int kSliceBits = 23;           // 2^23 u32 counters = 32 MiB per slice (64 MiB slices get written back 4.5x: profiles/)
 constexpr int kMaxBuckets = 64;
-constexpr int kChunk = 2048;             // entries per apply ticket (8 per thread)
+#ifndef PG_CHUNK
+#define PG_CHUNK 1024
+#endif
+constexpr int kChunk = PG_CHUNK;         // entries per apply ticket (PG_CHUNK / 256 per thread)
 constexpr unsigned long long kOverflowRun = ~0ull;
-constexpr uint32_t kInvalidEntry = 0xFFFFFFFFu; // never a real entry: count entries have low bits 000, feature deltas stop at 510
+constexpr uint32_t kInvalidEntry = 0xFFFFFFFFu; // never a real entry: count entries have low bits 000, deltas stop at 510
 constexpr uint32_t kEntryIndexBits = 0x03FFFFF8u;
-constexpr int kMaxRowDelta = 510;
+constexpr int kMaxRowDelta = 509;      // 510 = count-only window of the shared partition, 511 = padding
 
 // tile shape of the scatter kernels: one word per thread
 template <bool FEAT>
@@ -214,20 +217,38 @@ struct ScatterSmem {
 
 struct ScatterParams {
     const uint64_t* codes;
-    const uint32_t* mask;      // count: maskC; feature: maskF (NOFEAT reads cleared)
+    const uint32_t* mask;      // count / shared: maskC; feature: maskF (NOFEAT reads cleared)
     int64_t w0, w1;            // segment of the stream, in words
     int k;
     BucketGeom geo;
     BucketState* st;
     uint32_t* entries;
-    int32_t* meta;             // feature: base row of every aligned group of 32 entries
-    uint32_t* table;           // count: the dense counters (overflow paths)
+    int32_t* meta;             // feature / shared: base row / base cloud of every aligned group of 32 entries
+    uint32_t* table;           // count / shared: the dense counters (overflow paths)
+    uint32_t* lost;            // shared: set to 1 when an overflow path applied counts directly - the entries of those
+                               // windows are missing from the buffer, so the featurize pass must not reuse it
 };
 
-template <int KT, bool FEAT>
-__global__ void __launch_bounds__(ScatterCfg<FEAT>::kThreads, ScatterCfg<FEAT>::kMinCtas)
+// MODE of the scatter kernel
+//   kScatterCount  : entries for the count pass only (maskC windows)
+//   kScatterFeat   : entries for the featurize pass only (feature windows of emitted clouds, 9-bit ROW delta);
+//                    words it cannot encode (3 clouds in a word, delta > 510) are looked up directly
+//   kScatterShared : ONE partition for both passes.  Every maskC window gets an entry; feature windows carry the
+//                    9-bit CLOUD delta against the tile's first cloud (rows are not known yet when counting:
+//                    the apply pass maps cloud -> row), count-only windows (lower-case bases, NOFEAT reads) the
+//                    reserved delta 511.  Needs maskF subset of maskC (no quality filter) and clouds of >= 64
+//                    bytes (<= 2 clouds per word, <= 257 per tile); the host checks both.
+enum { kScatterCount = 0, kScatterFeat = 1, kScatterShared = 2 };
+constexpr uint32_t kDeltaCountOnly = 510u; // never 511: with all index bits set that would read as kInvalidEntry
+
+__device__ __forceinline__ uint32_t delta_bits(uint32_t delta) { return ((delta >> 3) << 26) | (delta & 7u); }
+__device__ __forceinline__ uint32_t delta_of_entry(uint32_t e) { return ((e >> 26) << 3) | (e & 7u); }
+
+template <int KT, int MODE>
+__global__ void __launch_bounds__(ScatterCfg<MODE != kScatterCount>::kThreads, ScatterCfg<MODE != kScatterCount>::kMinCtas)
 bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
 {
+    constexpr bool FEAT = MODE != kScatterCount; // entry format with delta bits, runs padded to 32 + base per group
     using Cfg = ScatterCfg<FEAT>;
     constexpr int CAP = Cfg::kStageCap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -244,16 +265,20 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
         const int64_t tile0 = Q.w0 + t * Cfg::kTileWords;
         const int64_t j = tile0 + threadIdx.x;
         uint64_t lo = 0, hi = 0;
-        // a word holds windows of at most two clouds on the fast path: [0, split) -> (valid, row, D) and
-        // [split, 32) -> (valid2, row2, D2); valid2 != 0 only for the one word per cloud that holds its end
-        uint32_t valid = 0u, row = 0u, D = 0u, valid2 = 0u, row2 = 0u, D2 = 0u;
-        int32_t tile_row0 = 0;
-        if (FEAT) tile_row0 = __ldg(P.row_lb + (__ldg(P.wg + tile0) & ~kWordMixed));
+        // up to three trips over the 32 windows of the word, each with its own delta bits:
+        //   (v0, d0) windows of the word's first cloud   (count mode: all windows, no delta)
+        //   (v1, d1) windows of the cloud that starts inside the word (one word per cloud)
+        //   (v2, d2) shared mode: count-only windows
+        uint32_t v0 = 0u, d0 = 0u, v1 = 0u, d1 = 0u, v2 = 0u;
+        uint32_t row0 = 0u, row1 = 0u;  // feat mode: rows of the first two trips (overflow redo)
+        int32_t tile_base = 0;          // feat: rows emitted before the tile's first cloud; shared: the tile's first cloud
+        if (MODE == kScatterFeat) tile_base = __ldg(P.row_lb + (__ldg(P.wg + tile0) & ~kWordMixed));
+        if (MODE == kScatterShared) tile_base = (int32_t)(__ldg(P.wg + tile0) & ~kWordMixed);
         if (j < Q.w1) {
             const uint32_t mlo = __ldg(Q.mask + j);
             if (mlo != 0u) {
-                valid = window_valid_mask(mlo, __ldg(Q.mask + j + 1), k);
-                if (FEAT && valid) {
+                v0 = window_valid_mask(mlo, __ldg(Q.mask + j + 1), k);
+                if (MODE == kScatterFeat && v0) {
                     const uint32_t gw = __ldg(P.wg + j);
                     const uint32_t g = gw & ~kWordMixed;
                     int32_t r = __ldg(P.row_of_group + g), r2 = -1;
@@ -263,43 +288,55 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                         const int64_t split = __ldg(P.gstart + g + 1) - j * 32;
                         slow = (int64_t)g + 2 < P.n_groups && __ldg(P.gstart + g + 2) < (j + 1) * 32;
                         r2 = __ldg(P.row_of_group + g + 1);
-                        valid2 = valid & ~((1u << split) - 1u);
-                        valid &= (1u << split) - 1u;
+                        v1 = v0 & ~((1u << split) - 1u);
+                        v0 &= (1u << split) - 1u;
                     }
-                    if (r < 0) valid = 0u;   // dropped cloud
-                    if (r2 < 0) valid2 = 0u;
-                    if ((valid && r - tile_row0 > kMaxRowDelta) || (valid2 && r2 - tile_row0 > kMaxRowDelta)) slow = true;
+                    if (r < 0) v0 = 0u;   // dropped cloud
+                    if (r2 < 0) v1 = 0u;
+                    if ((v0 && r - tile_base > kMaxRowDelta) || (v1 && r2 - tile_base > kMaxRowDelta)) slow = true;
                     if (slow) {
-                        feat_word_direct(P, j, g, __ldg(Q.codes + j), __ldg(Q.codes + j + 1), valid | valid2);
-                        valid = valid2 = 0u;
+                        feat_word_direct(P, j, g, __ldg(Q.codes + j), __ldg(Q.codes + j + 1), v0 | v1);
+                        v0 = v1 = 0u;
                     } else {
-                        row = (uint32_t)r; row2 = (uint32_t)r2;
-                        const uint32_t d1 = (uint32_t)(r - tile_row0), d2 = (uint32_t)(r2 - tile_row0);
-                        D = ((d1 >> 3) << 26) | (d1 & 7u);
-                        D2 = ((d2 >> 3) << 26) | (d2 & 7u);
+                        row0 = (uint32_t)r; row1 = (uint32_t)r2;
+                        d0 = delta_bits((uint32_t)(r - tile_base));
+                        d1 = delta_bits((uint32_t)(r2 - tile_base));
                     }
                 }
-                if (valid | valid2) { lo = __ldg(Q.codes + j); hi = __ldg(Q.codes + j + 1); }
+                if (MODE == kScatterShared && v0) {
+                    const uint32_t gw = __ldg(P.wg + j);
+                    const uint32_t delta = (gw & ~kWordMixed) - (uint32_t)tile_base;
+                    const uint32_t mf = __ldg(P.maskF + j);
+                    const uint32_t vf = mf ? (window_valid_mask(mf, __ldg(P.maskF + j + 1), k) & v0) : 0u;
+                    v2 = v0 & ~vf;
+                    v0 = vf;
+                    d0 = delta_bits(delta);
+                    if (gw & kWordMixed) {
+                        const int64_t split = __ldg(P.gstart + (gw & ~kWordMixed) + 1) - j * 32;
+                        v1 = vf & ~((1u << split) - 1u);
+                        v0 = vf & ((1u << split) - 1u);
+                        d1 = delta_bits(delta + 1u);
+                    }
+                }
+                if (v0 | v1 | v2) { lo = __ldg(Q.codes + j); hi = __ldg(Q.codes + j + 1); }
             }
         }
         // every lane issues the atomic: windows that emit nothing go to the dummy row, so the loop has
         // no divergence bookkeeping (a conditional shared atomic compiles to BSSY/BRA/ATOMS/BSYNC)
-        {
-            uint32_t v = valid ? valid : valid2, d = valid ? D : D2;
-            const uint32_t v_next = valid ? valid2 : 0u;
-            while (v != 0u) { // second trip only for a word that holds a cloud boundary
-                // ptxas would hoist the 32 loop-invariant window extractions out of this loop and spill them: a shuffle
-                // from the own lane is the identity, but not one the optimiser can see through (2 SHFL per 32 windows)
-                lo = __shfl_sync(__activemask(), lo, lane);
-                hi = __shfl_sync(__activemask(), hi, lane);
-                for_each_window<KT>(lo, hi, k, [&](int i, uint32_t y) {
-                    const uint32_t b = (v & (1u << i)) ? (y >> 26) : (uint32_t)kMaxBuckets;
-                    const uint32_t slot = min(atomicAdd(cnt + b, 1u), (uint32_t)(CAP - 1)); // a row that overflows is redone below
-                    stage[b * CAP + slot] = FEAT ? ((y & kEntryIndexBits) | d) : y;
-                });
-                v = (v == v_next) ? 0u : v_next;
-                d = D2;
-            }
+#pragma unroll 1
+        for (int trip = 0; trip < (MODE == kScatterCount ? 1 : MODE == kScatterFeat ? 2 : 3); ++trip) {
+            const uint32_t v = trip == 0 ? v0 : trip == 1 ? v1 : v2;
+            const uint32_t d = trip == 0 ? d0 : trip == 1 ? d1 : delta_bits(kDeltaCountOnly);
+            if (v == 0u) continue; // trips 1 and 2 are rare: one word per cloud / lower-case bases
+            // ptxas would hoist the 32 loop-invariant window extractions out of this loop and spill them: a shuffle
+            // from the own lane is the identity, but not one the optimiser can see through (2 SHFL per 32 windows)
+            lo = __shfl_sync(__activemask(), lo, lane);
+            hi = __shfl_sync(__activemask(), hi, lane);
+            for_each_window<KT>(lo, hi, k, [&](int i, uint32_t y) {
+                const uint32_t b = (v & (1u << i)) ? (y >> 26) : (uint32_t)kMaxBuckets;
+                const uint32_t slot = min(atomicAdd(cnt + b, 1u), (uint32_t)(CAP - 1)); // a row that overflows is redone below
+                stage[b * CAP + slot] = FEAT ? ((y & kEntryIndexBits) | d) : y;
+            });
         }
         __syncthreads();
 
@@ -344,38 +381,49 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                     if (e + 3u >= n) v.w = kInvalidEntry;
                     __stcs(dst + (e >> 2), v);
                 }
-                if (FEAT && (uint32_t)lane < (n_pad >> 5)) Q.meta[(gb >> 5) + lane] = tile_row0;
-            } else if (FEAT) { // region full: look the run up here (whole warp stays in the loop for the reduction)
+                if (FEAT && (uint32_t)lane < (n_pad >> 5)) Q.meta[(gb >> 5) + lane] = tile_base;
+            } else if (MODE == kScatterFeat) { // region full: look the run up here (whole warp stays in the loop for the reduction)
                 for (uint32_t e0 = 0; e0 < n; e0 += 32) {
                     const uint32_t e = e0 + lane;
                     unsigned long long key = 0;
                     bool live = false;
                     if (e < n) {
                         const uint32_t v = src[e];
-                        const uint32_t r = (uint32_t)tile_row0 + (((v >> 26) << 3) | (v & 7u));
+                        const uint32_t r = (uint32_t)tile_base + delta_of_entry(v);
                         live = abd_key(P, __ldg(P.table.counts + (((uint32_t)b << kSliceBits) | ((v >> 3) & Q.geo.low_mask))), r, key);
                     }
                     abd_reduce_warp(P, live, key);
                 }
             } else { // region full: apply the run here
-                for (uint32_t e = lane; e < n; e += 32) atomicAdd(Q.table + (src[e] >> 3), 1u);
+                for (uint32_t e = lane; e < n; e += 32) atomicAdd(Q.table + (((uint32_t)b << kSliceBits) | ((src[e] >> 3) & Q.geo.low_mask)), 1u);
+                if (MODE == kScatterShared && lane == 0) *Q.lost = 1u;
             }
         }
 
         // ---- staging rows that overflowed: walk the tile again, those slices go straight to the table ----
         const unsigned long long ovf = S.ovf;
-        if (ovf != 0ull && (valid | valid2) != 0u) {
+        if (ovf != 0ull && (v0 | v1 | v2) != 0u) {
             for (int i = 0; i < 32; ++i) {
-                if (!(((valid | valid2) >> i) & 1u)) continue;
+                if (!(((v0 | v1 | v2) >> i) & 1u)) continue;
                 const uint32_t y = window_y(lo, hi, i, k);
                 if (!((ovf >> (y >> 26)) & 1ull)) continue;
-                if (FEAT) abd_direct(P, y, ((valid >> i) & 1u) ? row : row2);
+                if (MODE == kScatterFeat) abd_direct(P, y, ((v0 >> i) & 1u) ? row0 : row1);
                 else atomicAdd(Q.table + (y >> 3), 1u);
             }
+            if (MODE == kScatterShared) *Q.lost = 1u;
         }
         __syncthreads();
     }
 }
+
+// entries per region after a scatter launch (the cursors are reset for the next segment)
+__global__ void bucket_save_fill_kernel(const BucketState* st, BucketGeom geo, unsigned long long* fill_out)
+{
+    if (threadIdx.x < kMaxBuckets)
+        fill_out[threadIdx.x] = (int)threadIdx.x < geo.n_buckets ? min(min(st->cursors[threadIdx.x], st->limits[threadIdx.x]), geo.cap) : 0ull;
+}
+
+__global__ void bucket_reset_ticket_kernel(BucketState* st) { st->ticket = 0ull; }
 
 // ---------------------------------------------------------------------------
 // apply: ordered tickets over the filled part of every region: ticket -> (slice, offset)
@@ -386,12 +434,13 @@ struct ApplySmem {
     unsigned long long ticket;
 };
 
-__device__ __forceinline__ void apply_prologue(ApplySmem& A, const BucketGeom& geo, const BucketState* st)
+// saved_fill != nullptr: regions of an earlier scatter launch whose fills were kept (bucket_save_fill_kernel)
+__device__ __forceinline__ void apply_prologue(ApplySmem& A, const BucketGeom& geo, const BucketState* st, const unsigned long long* saved_fill = nullptr)
 {
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
         for (int b = 0; b < geo.n_buckets; ++b) {
-            const unsigned long long f = min(min(st->cursors[b], st->limits[b]), geo.cap);
+            const unsigned long long f = saved_fill ? saved_fill[b] : min(min(st->cursors[b], st->limits[b]), geo.cap);
             A.fill[b] = f;
             A.chunk_base[b] = acc;
             acc += (f + kChunk - 1) / kChunk;
@@ -448,12 +497,14 @@ bucket_apply_count_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, 
 // sweep the partitioned entries slice by slice: gather (L2 hit), bin, reduce.
 // The ticket of the NEXT chunk is requested before the current chunk is processed and read when it
 // is done, so the round trip of the global atomic is hidden behind the chunk's own work.
+// SHARED: the entries come from the shared partition of the count pass (cloud deltas; cloud -> row here)
+template <bool SHARED>
 __global__ void __launch_bounds__(256)
 bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __restrict__ meta, BucketGeom geo,
-                         BucketState* __restrict__ st, const FeatParams P)
+                         BucketState* __restrict__ st, const unsigned long long* __restrict__ saved_fill, const FeatParams P)
 {
     __shared__ ApplySmem A;
-    apply_prologue(A, geo, st);
+    apply_prologue(A, geo, st, SHARED ? saved_fill : nullptr);
     const unsigned long long n_chunks = A.chunk_base[geo.n_buckets];
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
@@ -481,19 +532,25 @@ bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __
         }
 #pragma unroll
         for (int u = 0; u < kChunk / 256; ++u)
-            cnt[u] = e[u] != kInvalidEntry ? __ldg(slice + ((e[u] >> 3) & geo.low_mask)) : 0u;
+            cnt[u] = (e[u] != kInvalidEntry && !(SHARED && delta_of_entry(e[u]) == kDeltaCountOnly)) ? __ldg(slice + ((e[u] >> 3) & geo.low_mask)) : 0u;
 #pragma unroll
         for (int u = 0; u < kChunk / 256; ++u) {
             // the 32 entries of a warp share row0: (delta, bin) identifies the tally inside the warp in 22 bits
-            const uint32_t delta = ((e[u] >> 26) << 3) | (e[u] & 7u);
+            const uint32_t delta = delta_of_entry(e[u]);
             uint32_t c32 = cnt[u] & kCountMask;
-            const bool live = cnt[u] != 0u && c32 < P.clamp; // absent k-mers are skipped (count_kmer.cpp:87); cnt = 0 for padding
+            bool live = cnt[u] != 0u && c32 < P.clamp; // absent k-mers are skipped (count_kmer.cpp:87); cnt = 0 for padding
+            int32_t row = row0[u] + (int32_t)delta;
+            if (SHARED) { // row0 is the tile's first cloud: cloud -> row (lanes of a warp hit 1-3 addresses); dropped clouds fall out here
+                live = live && delta != kDeltaCountOnly;
+                row = live ? __ldg(P.row_of_group + row) : -1;
+                live = row >= 0;
+            }
             const uint32_t key = (delta << 13) | (live ? abd_bin(P, c32) : 0u); // vector_size <= 8192
             const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
             if (live) {
                 const uint32_t peers = __match_any_sync(live_mask, key);
                 if (lane == __ffs(peers) - 1)
-                    atomicAdd(P.abd + (int64_t)((uint32_t)row0[u] + delta) * P.vs + (key & 0x1FFFu), (uint32_t)__popc(peers));
+                    atomicAdd(P.abd + (int64_t)row * P.vs + (key & 0x1FFFu), (uint32_t)__popc(peers));
             }
         }
         if (threadIdx.x == 0) A.ticket = next;
