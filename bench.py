@@ -194,7 +194,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # algorithmic bytes (DESIGN.md "Roofline")
 # --------------------------------------------------------------------------------------
-def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows, sliced, vs=400, td=136):
+def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows, sliced, vs=400, td=136, shared=False, count_segments=1,
+                      table_bytes=2 ** 31):
     """Bytes each kernel has to move by design (DESIGN.md "Kernels and rooflines").  stream =
     2-bit codes + 1 validity bit per base position.  With the L2-sliced table (k = 15) a pass is
     two kernels: scatter writes one entry per window, apply reads it back and touches the counter."""
@@ -202,21 +203,24 @@ def algorithmic_bytes(n_bytes, entries_count, windows_count, windows_feat, rows,
     out = 4.0 * rows * (vs + td)
     b = {"pack": n_bytes * (1.0 + 0.25 + 2 * 0.125), "normalize": 2 * out}
     if sliced:
-        b["count_scatter"] = n_bytes * stream + 4.0 * entries_count
+        # shared partition (one scatter for both passes): two mask streams in, 4 B per window + one i32 per 32 entries out
+        b["count_scatter"] = n_bytes * (stream + (0.125 + 0.125 if shared else 0.0)) + (4.125 if shared else 4.0) * entries_count
         b["count_split"] = 4.0 * entries_count + 2.0 * entries_count       # second partition level: u32 in, u16 out
-        b["count_apply"] = 2.0 * entries_count + 8.0 * windows_count      # entry + u32 counter read-modify-write per window
+        # shared-memory sub-slice tables: 2 B per entry in, the table read and written once per segment
+        b["count_apply"] = 2.0 * entries_count + 2.0 * table_bytes * count_segments
         b["tnf"] = n_bytes * stream + 4.0 * rows * td
-        b["feat_scatter"] = n_bytes * stream + 4.0 * windows_feat
-        b["feat_apply"] = 4.0 * windows_feat + 4.0 * windows_feat + 4.0 * rows * vs   # entry + u32 counter read per window, tallies out
+        if not shared:
+            b["feat_scatter"] = n_bytes * stream + 4.125 * windows_feat
+        b["feat_apply"] = 4.125 * windows_feat + 4.0 * windows_feat + 4.0 * rows * vs   # entry + u32 counter read per window, tallies out
     else:
         b["count_apply"] = n_bytes * stream + 8.0 * windows_count
         b["feat_apply"] = n_bytes * stream + 4.0 * windows_feat + out
     return b
 
 
-KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,false>", "count_split": "bucket_split_kernel",
+KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,shared>", "count_split": "bucket_split_kernel",
                    "count_apply": "sub_apply_kernel", "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
-                   "feat_scatter": "bucket_scatter_kernel<15,true>", "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
+                   "feat_scatter": "bucket_scatter_kernel<15,feat>", "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
 STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_split", 9), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
                ("normalize", 4))
 
@@ -370,11 +374,15 @@ def main():
     if windows_count is None:
         windows_count = windows_feat
     sliced = stage_ms["count_scatter"] > 0
-    alg = algorithmic_bytes(batch_data["n_bytes"], windows_count, windows_count, windows_feat, rows, sliced)
+    shared = sliced and stage_ms["feat_scatter"] == 0
+    alg = algorithmic_bytes(batch_data["n_bytes"], windows_count, windows_count, windows_feat, rows, sliced, shared=shared,
+                            count_segments=max(1, stage_launches["count_apply"] // 2))
     peak, peak_src = load_peaks()
     dom = max((n for n in alg if n in stage_ms), key=lambda n: stage_ms[n])
     kname = KERNEL_OF_STAGE[dom] if sliced else {"count_apply": "count_kernel", "feat_apply": "featurize_kernel"}.get(dom, KERNEL_OF_STAGE[dom])
-    n_launch = max(1, stage_launches[dom] - (stage_launches[dom] // 2 if dom.endswith("scatter") else 0))  # scatter spans include the reset kernel
+    # spans of the scatter / split / count-apply stages also hold one housekeeping launch per segment (reset, fill save, item scan)
+    per_seg = {"count_scatter": 3 if shared else 2, "feat_scatter": 2, "count_split": 2, "count_apply": 2}.get(dom, 1)
+    n_launch = max(1, stage_launches[dom] // per_seg)
     achieved = alg[dom] / (stage_ms[dom] / 1e3) / 1e9
     b_pair = 2456.0 if args.read_len == 100 else 3832.0
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

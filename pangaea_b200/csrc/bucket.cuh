@@ -264,6 +264,18 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
 
         const int64_t tile0 = Q.w0 + t * Cfg::kTileWords;
         const int64_t j = tile0 + threadIdx.x;
+        {   // the tile this CTA walks next is far ahead in the stream: pull its lines into L2 now (no registers held),
+            // so that the dependent loads at the top of the next trip are L2 hits instead of DRAM round trips
+            const int64_t jn = j + (int64_t)gridDim.x * Cfg::kTileWords;
+            if (jn < Q.w1) {
+                if ((threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Q.codes + jn));
+                if ((threadIdx.x & 31) == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Q.mask + jn));
+                    if (FEAT) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.wg + jn));
+                    if (MODE == kScatterShared) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.maskF + jn));
+                }
+            }
+        }
         uint64_t lo = 0, hi = 0;
         // up to three trips over the 32 windows of the word, each with its own delta bits:
         //   (v0, d0) windows of the word's first cloud   (count mode: all windows, no delta)

@@ -48,6 +48,13 @@ tnf_kernel(const FeatParams P)
         const uint32_t g_lo = __ldg(P.wg + tile) & ~kWordMixed;
         const uint32_t g_hi = __ldg(P.wg + tile_end - 1) & ~kWordMixed; // clouds of the uniform words: g_lo .. g_hi
         const int64_t j = tile + threadIdx.x;
+        if (j + kTnfThreads < w_end) { // next tile of this CTA -> L2 while this one is tallied
+            if ((threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.codes + j + kTnfThreads));
+            if ((threadIdx.x & 31) == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.maskF + j + kTnfThreads));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.wg + j + kTnfThreads));
+            }
+        }
         uint32_t mlo = 0u;
         if (j < tile_end) mlo = __ldg(P.maskF + j);
         if (mlo != 0u) {

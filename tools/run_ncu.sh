@@ -1,8 +1,11 @@
-# usage: bash tools/run_ncu.sh <tag> [pairs] [skip] [count] - plain run first, then one ncu --set full capture of the hot kernels
-# defaults capture one launch of every hot kernel of the 4th step at the headline workload (37 matching launches per step)
-TAG=${1:-r01}; PAIRS=${2:-50000000}; SKIP=${3:-111}; COUNT=${4:-19}
+# usage: bash tools/run_ncu.sh <tag> - plain run first, then ncu --set full captures of one launch of every hot kernel of the
+# 4th step at the headline workload (after 3 warm-up steps).  Matching launches per step: pack 1 + 5 x (scatter, save_fill, split,
+# sub_apply) in the first capture; tnf 1 + 5 x apply_feat in the second.
+TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --pairs $PAIRS --no-cpu-baseline --no-e2e"
-$CMD > gpurun_out/plain_$TAG.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'bucket_s|bucket_apply|tnf_kernel|pack_kernel|sub_apply' -s $SKIP -c $COUNT -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
-echo "exit $?"; tail -3 gpurun_out/ncu_$TAG.log | cut -c1-300
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+$CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; exit 1; }
+timeout 900 ncu --set full --clock-control none -k regex:'bucket_s|pack_kernel|sub_apply' -s 63 -c 5 -o gpurun_out/prof_${TAG}_count -f $CMD > gpurun_out/ncu_${TAG}_count.log 2>&1
+echo "exit $?"
+timeout 900 ncu --set full --clock-control none -k regex:'tnf_kernel|bucket_apply_feat' -s 18 -c 2 -o gpurun_out/prof_${TAG}_feat -f $CMD > gpurun_out/ncu_${TAG}_feat.log 2>&1
+echo "exit $?"; ls -la gpurun_out/*.ncu-rep
