@@ -56,6 +56,9 @@ struct ScatterCfg {
     static constexpr int kTileWords = kThreads;
     // staging slots per slice per tile: mean = 32 * kThreads / 64 (128 / 256) + > 5 sigma of the binomial
     static constexpr int kStageCap = FEAT ? 352 : 192;
+    // words per staging row: + 4 so that consecutive rows start 4 banks apart (all rows fill at the same pace; with
+    // a stride that is a multiple of 32 words the lanes of a store would crowd the banks of the current fill level)
+    static constexpr int kStageStride = kStageCap + 4;
     static constexpr int kMinCtas = FEAT ? 2 : 4;
     // runs are padded with kInvalidEntry to a multiple of this, so that they start 16 B aligned and are copied
     // out with 128-bit stores (feature runs: 32, because every aligned group of 32 entries shares one base row)
@@ -212,7 +215,7 @@ struct ScatterSmem {
     uint32_t n_run[kMaxBuckets];           // entries to copy out per slice (0 when the staging row overflowed)
     unsigned long long gbase[kMaxBuckets]; // where this tile's run starts in the entry buffer
     unsigned long long ovf;                // bit b: the staging row of slice b overflowed in this tile
-    alignas(16) uint32_t stage[(kMaxBuckets + 1) * ScatterCfg<FEAT>::kStageCap];
+    alignas(16) uint32_t stage[(kMaxBuckets + 1) * ScatterCfg<FEAT>::kStageStride];
 };
 
 struct ScatterParams {
@@ -250,7 +253,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
 {
     constexpr bool FEAT = MODE != kScatterCount; // entry format with delta bits, runs padded to 32 + base per group
     using Cfg = ScatterCfg<FEAT>;
-    constexpr int CAP = Cfg::kStageCap;
+    constexpr int CAP = Cfg::kStageCap, STRIDE = Cfg::kStageStride;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem<FEAT>& S = *reinterpret_cast<ScatterSmem<FEAT>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -347,7 +350,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             for_each_window<KT>(lo, hi, k, [&](int i, uint32_t y) {
                 const uint32_t b = (v & (1u << i)) ? (y >> 26) : (uint32_t)kMaxBuckets;
                 const uint32_t slot = min(atomicAdd(cnt + b, 1u), (uint32_t)(CAP - 1)); // a row that overflows is redone below
-                stage[b * CAP + slot] = FEAT ? ((y & kEntryIndexBits) | d) : y;
+                stage[b * STRIDE + slot] = FEAT ? ((y & kEntryIndexBits) | d) : y;
             });
         }
         __syncthreads();
@@ -380,7 +383,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
         for (int b = warp; b < Q.geo.n_buckets; b += Cfg::kThreads / 32) {
             const uint32_t n = S.n_run[b];
             if (!n) continue;
-            const uint32_t* src = stage + b * CAP;
+            const uint32_t* src = stage + b * STRIDE;
             const unsigned long long gb = S.gbase[b];
             if (gb != kOverflowRun) {
                 const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);

@@ -30,6 +30,9 @@ constexpr int kSplitThreads = 512;
 constexpr int kSplitPer = 32;                                // entries per thread
 constexpr int kSplitTile = kSplitThreads * kSplitPer;        // 16384 entries: 64 per sub-slice
 constexpr int kSplitCap = 128;                               // staging slots per sub-slice per tile (mean 64 + 8 sigma)
+constexpr int kSplitStride = 136;                            // u16 per staging row: 68 words, so that rows start on different banks (all
+                                                             // rows fill at the same pace: with a stride of 64 words the 32 lanes of a
+                                                             // store would pile onto the few banks of the current fill level)
 constexpr int kSubApplyThreads = 1024;
 constexpr uint32_t kSubOverflow = 0xFFFFFFFFu;
 constexpr uint16_t kSubInvalid = 0x8000u;                    // padding entry: runs start 16 B aligned (8 entries); lands in a dummy counter
@@ -58,7 +61,7 @@ struct SplitSmem {
     uint32_t ovf[kSubFan / 32];           // staging rows that overflowed in this tile
     unsigned long long fill[kMaxBuckets];
     unsigned long long tile_base[kMaxBuckets + 1];
-    alignas(16) uint16_t stage[(kSubFan + 1) * kSplitCap];
+    alignas(16) uint16_t stage[(kSubFan + 1) * kSplitStride];
 };
 
 __global__ void __launch_bounds__(kSplitThreads, 2)
@@ -105,7 +108,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
             for (int c = 0; c < 4; ++c) {
                 const uint32_t sub = (i0 + c < n && v[c] != kInvalidEntry) ? ((v[c] >> (3 + kSubBits)) & (kSubFan - 1)) : (uint32_t)kSubFan;
                 const uint32_t slot = min(atomicAdd(cnt + sub, 1u), (uint32_t)(kSplitCap - 1));
-                stage[sub * kSplitCap + slot] = (uint16_t)((v[c] >> 3) & (kSubWords - 1));
+                stage[sub * kSplitStride + slot] = (uint16_t)((v[c] >> 3) & (kSubWords - 1));
             }
         }
         __syncthreads();
@@ -131,7 +134,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
         for (int s = 4 * warp + (lane >> 3); s < kSubFan; s += kSplitThreads / 8) {
             const uint32_t m = S.n_run[s];
             if (!m) continue;
-            const uint16_t* row = stage + s * kSplitCap;
+            const uint16_t* row = stage + s * kSplitStride;
             const uint32_t o = S.off[s];
             if (o != kSubOverflow) {
                 uint4* dst = reinterpret_cast<uint4*>(entries2 + (unsigned long long)(b * kSubFan + s) * sg.cap + o);
