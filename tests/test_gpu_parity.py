@@ -403,3 +403,71 @@ def test_properties_at_scale():
     a, t, w = f1.normalized()
     assert np.allclose(a.sum(axis=1), 1, atol=1e-5) and np.allclose(t.sum(axis=1), 1, atol=1e-5)
     assert (w > 0).all() and (w <= 1).all()
+
+
+# ------------------------------------------------------------------------------------
+# the other BASELINE.json configurations as parity cases (reduced sizes)
+# ------------------------------------------------------------------------------------
+def test_config_tellseq_2x150_18bp_barcodes(tmp_path, oracle):
+    """configs[2]: TELL-Seq after preprocessing - 2x150 bp, 18-bp barcodes in the BX tag."""
+    data = synth.generate(n_barcodes=400, mean_pairs=12, read_len=150, n_genomes=4, genome_len=120_000, frag_len=20_000,
+                          barcode_len=18, seed=3, unbarcoded_pairs=30)
+    path = synth.write_interleaved(str(tmp_path / "tell.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    fq = _lib.Fastq(path)
+    ctx = _ctx()
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    g_abd, g_tnf = feats.raw()
+    assert _names(fq, feats) == list(names) and len(names) > 300 and all(len(n) == 18 for n in names)
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+
+
+@pytest.mark.parametrize("env", [{}, {"PG_NO_SHARED": "1"}])
+def test_config_hybrid_one_cloud_per_pair(tmp_path, oracle, monkeypatch, env):
+    """configs[3]: plain short reads, every pair its own (virtual) barcode, min_length 0 - the reference-equivalent of
+    per-read features.  Clouds are 302 bytes: a cloud boundary falls into every 10th word and a 512-word
+    tile spans ~55 clouds (TNF slots overflow to global reductions)."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    data = synth.generate(n_barcodes=3000, mean_pairs=1, read_len=150, n_genomes=3, genome_len=100_000, frag_len=5_000, seed=4)
+    keep_one = np.concatenate([[True], np.array(data["barcode"][1:]) != np.array(data["barcode"][:-1])])  # first pair of every barcode
+    data = {"seq1": data["seq1"][keep_one], "seq2": data["seq2"][keep_one], "barcode": [b for b, k in zip(data["barcode"], keep_one) if k],
+            "read_len": 150, "n_pairs": int(keep_one.sum())}
+    path = synth.write_interleaved(str(tmp_path / "hybrid.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None, mlen=0)
+    fq = _lib.Fastq(path)
+    ctx = _ctx(min_length=0)
+    feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+    g_abd, g_tnf = feats.raw()
+    assert _names(fq, feats) == list(names) and len(names) == data["n_pairs"] - 1  # the quirk drops the last label
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    assert (g_tnf.sum(axis=1) <= 2 * 147).all()  # one pair per row
+
+
+def test_shared_partition_equals_separate_partitions_at_scale(monkeypatch):
+    """The shared partition of pg_count (reused by pg_featurize) and the two separate partitions give identical tables
+    and matrices on 1.5 M device-generated 2x150 pairs - including lower-case-free count-only handling and dropped clouds."""
+    import torch
+
+    from bench import make_synthetic_batch
+
+    results = []
+    for no_shared in ("0", "1"):
+        monkeypatch.setenv("PG_NO_SHARED", no_shared)
+        ctx = _ctx(min_length=30_200)  # drops about half of the clouds (Poisson(100) pairs x 302 bytes)
+        s = make_synthetic_batch(ctx, n_pairs=1_500_000, read_len=150, n_barcodes=15_000, n_genomes=10, genome_len=400_000, seed=11)
+        batch = ctx.adopt(s["reads"], keepalive=s)
+        ctx.count(batch)
+        keep = np.ones(s["n_groups"], np.uint8)
+        keep[0] = 0
+        keep[5::7] = 0  # some clouds dropped by label as well
+        f = ctx.featurize(batch, keep)
+        abd, tnf = f.raw()
+        results.append((abd, tnf, f.row_groups(), int(ctx.table_as_torch().to(torch.int64).sum()), ctx.table_size()))
+        stages = {n: ctx.timing(w)[0] for n, w in (("count_scatter", _lib.T_COUNT_SCATTER), ("feat_scatter", _lib.T_FEAT_SCATTER))}
+        assert (stages["feat_scatter"] == 0) == (no_shared == "0")  # the shared path really ran / was really switched off
+        f.free(); batch.free(); ctx.close()
+    (a0, t0, g0, s0, n0), (a1, t1, g1, s1, n1) = results
+    assert 3000 < len(g0) < 14000 and np.array_equal(g0, g1)
+    assert s0 == s1 and n0 == n1
+    assert np.array_equal(a0, a1) and np.array_equal(t0, t1)
