@@ -99,3 +99,43 @@ def test_long_lines_and_chunk_boundaries(tmp_path, oracle):
     assert np.diff(off).tolist() == [len(big) + 1, 5, 70001, 5]
     assert flag.tolist() == [0, 1, 0, 1] and keep.tolist() == [0, 1, 1]
     assert bytes(seq[off[2]:off[3]]) == big[:70000] + b"\n"
+
+
+def _parse_all(path, want_qual=False):
+    fq = _lib.Fastq(path, want_qual=want_qual)
+    seq, off, flag, keep = (a.copy() for a in fq.arrays())
+    r = fq.reads
+    qual = bytes(np.ctypeslib.as_array(C.cast(r.qual, C.POINTER(C.c_uint8)), shape=(r.n_bytes,))) if want_qual and r.n_bytes else b""
+    labels = [fq.label(g) for g in range(fq.n_groups)]
+    fq.close()
+    return seq, off, flag, keep, labels, qual
+
+
+@pytest.mark.parametrize("threads", ["2", "3", "7", "16"])
+def test_parallel_reader_equals_sequential_reader(tmp_path, monkeypatch, threads):
+    """The multi-threaded reader of plain-text interleaved files (fastq.cpp: parse_interleaved_parallel) takes the same
+    decisions as the sequential loop: golden files of the reference tools (ragged / hostile text included), a stLFR file
+    whose read_type latches late, a truncated last record, barcodes that change exactly at the thread cuts."""
+    from pangaea_b200 import synth
+
+    files = [os.path.join(ROOT, "tests", "golden", d, "reads.fq") for d in ("kat1_interleaved_10x", "edge_ragged", "synth_10x_l2000")]
+    data = synth.generate(n_barcodes=40, mean_pairs=3, read_len=37, n_genomes=2, genome_len=5000, frag_len=1000, seed=5, unbarcoded_pairs=7)
+    files.append(synth.write_interleaved(str(tmp_path / "stlfr.fq"), data, style="stlfr"))
+    # headers without any barcode first, then stLFR ones: the type latches in the middle of the file
+    late = b"".join(b"@p%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(10)) + open(files[-1], "rb").read()
+    (tmp_path / "late.fq").write_bytes(late)
+    files.append(str(tmp_path / "late.fq"))
+    (tmp_path / "trunc.fq").write_bytes(open(files[0], "rb").read()[:-37])  # ends inside a record, no final newline
+    files.append(str(tmp_path / "trunc.fq"))
+    (tmp_path / "one.fq").write_bytes(b"@a BX:Z:AA-1\nACGT\n+\nIIII\n@a BX:Z:AA-1\nGG\n+\n>>")
+    files.append(str(tmp_path / "one.fq"))
+    for path in files:
+        monkeypatch.setenv("PG_FASTQ_THREADS", "1")
+        want = _parse_all(path, want_qual=True)
+        monkeypatch.setenv("PG_FASTQ_THREADS", threads)
+        monkeypatch.setenv("PG_FASTQ_PARALLEL_MIN", "0")
+        got = _parse_all(path, want_qual=True)
+        monkeypatch.delenv("PG_FASTQ_PARALLEL_MIN")
+        for a, b in zip(want[:4], got[:4]):
+            assert np.array_equal(a, b), path
+        assert want[4] == got[4] and want[5] == got[5], path
