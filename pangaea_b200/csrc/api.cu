@@ -1110,7 +1110,13 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
         if (sliced) {
             // ---- L2-sliced path: TNF kernel, then partition of the window indices and slice-by-slice look-ups ----
             {
-                const size_t smem_t = ((size_t)kSlots * ((size_t)1 << (2 * P.tnf_k)) + 2) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
+                const size_t nb = (size_t)1 << (2 * P.tnf_k);
+                // cloud slots with private bins: enough for the clouds an average 8 KB tile spans (4 for 20 KB clouds - more would
+                // only cost occupancy: 6.3 -> 8.6 ms - up to 32 for one cloud per read pair), within 32 KB of bins per CTA
+                const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
+                const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
+                P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
+                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb;
                 const int64_t max_cta = (int64_t)ctx->sm_count * 8;
                 const int64_t n_cta = std::min<int64_t>(max_cta, (b->n_words + kTnfThreads - 1) / kTnfThreads);
                 int64_t wpc = (b->n_words + n_cta - 1) / n_cta;

@@ -42,6 +42,7 @@ struct FeatParams {
     const uint32_t* wg;         // n_words: cloud of base 32 j | kWordMixed (scan.cuh) - sliced path and tnf.cuh
     const int32_t* row_lb;      // n_groups: rows emitted before cloud g
     int32_t tnf_k, vs, td;
+    int32_t tnf_slots;          // tnf.cuh: cloud slots with block-private bins
     uint32_t ws, clamp;         // clamp = min(ws * vs, 2^32-1): counts >= clamp fall outside the histogram
     uint32_t magic;             // ceil(2^32 / ws) when use_magic
     int32_t use_magic;

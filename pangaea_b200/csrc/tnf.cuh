@@ -11,7 +11,7 @@
 // 32 shared atomics of a word are issued without divergence.
 //
 // A CTA owns a contiguous range of words and keeps the bins of the clouds under its cursor
-// (kSlots of them; clouds much smaller than a tile overflow to global reductions).  Words
+// (kTnfSlots of them at tnf_k <= 4, fewer for wider windows; clouds beyond them go to global reductions).  Words
 // that hold a cloud boundary (scan.cuh: kWordMixed, one per cloud) resolve the cloud per
 // position and go straight to the global matrix.
 //
@@ -23,6 +23,7 @@
 namespace pg {
 
 constexpr int kTnfThreads = 256;
+constexpr int kTnfSlots = 32; // clouds of a 256-word tile with private bins: 1 KB each at tnf_k = 4 (one cloud per read pair still fits)
 
 template <int TK>
 __global__ void __launch_bounds__(kTnfThreads)
@@ -31,9 +32,10 @@ tnf_kernel(const FeatParams P)
     extern __shared__ uint32_t smem[];
     const int tk = TK ? TK : P.tnf_k;
     const int nb = 1 << (2 * tk);                                  // raw bins per slot
-    uint32_t* bins = smem;                                         // [kSlots][nb] + 1 dummy
-    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + kSlots * nb + 1);
-    for (int i = threadIdx.x; i < kSlots * nb + 1; i += blockDim.x) bins[i] = 0u;
+    const int n_slots = P.tnf_slots;                               // host: as many as fit (api.cu)
+    uint32_t* bins = smem;                                         // [n_slots][nb] + 1 dummy
+    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + n_slots * nb + 1);
+    for (int i = threadIdx.x; i < n_slots * nb + 1; i += blockDim.x) bins[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) lut_s[i] = P.lut[i];
     __syncthreads();
 
@@ -41,7 +43,7 @@ tnf_kernel(const FeatParams P)
     const int64_t w_end = min(P.n_words, w_begin + P.words_per_cta);
     if (w_begin >= w_end) return;
     const uint32_t tmask = (uint32_t)nb - 1u;
-    const uint32_t dummy = (uint32_t)(kSlots * nb);
+    const uint32_t dummy = (uint32_t)(n_slots * nb);
 
     for (int64_t tile = w_begin; tile < w_end; tile += kTnfThreads) {
         const int64_t tile_end = min(tile + (int64_t)kTnfThreads, w_end);
@@ -68,7 +70,7 @@ tnf_kernel(const FeatParams P)
                     const uint64_t lo = __ldg(P.codes + j), hi = __ldg(P.codes + j + 1);
                     const uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi;
                     const uint32_t slot = g - g_lo;
-                    if (slot < (uint32_t)kSlots) { // block-private bins
+                    if (slot < (uint32_t)n_slots) { // block-private bins
                         uint32_t* my = bins + slot * nb;
                         const uint32_t dmy = dummy - slot * nb;
 #pragma unroll
@@ -109,7 +111,7 @@ tnf_kernel(const FeatParams P)
         // slot 0 stays in shared memory while the next tile continues the same single cloud
         const bool carry = g_hi == g_lo && tile_end < w_end && (__ldg(P.wg + tile_end) & ~kWordMixed) == g_lo;
         if (!carry) {
-            const uint32_t ns = min((uint32_t)kSlots, g_hi - g_lo + 1u);
+            const uint32_t ns = min((uint32_t)n_slots, g_hi - g_lo + 1u);
             for (uint32_t s = 0; s < ns; ++s) {
                 const int32_t row = __ldg(P.row_of_group + g_lo + s);
                 if (row < 0) continue;

@@ -471,3 +471,38 @@ def test_shared_partition_equals_separate_partitions_at_scale(monkeypatch):
     assert 3000 < len(g0) < 14000 and np.array_equal(g0, g1)
     assert s0 == s1 and n0 == n1
     assert np.array_equal(a0, a1) and np.array_equal(t0, t1)
+
+
+def test_two_batches_one_table(tmp_path, oracle):
+    """Multi-batch flow of INTEGRATION.md: count every batch first (the table accumulates), then featurize each.  Both batches
+    keep their shared-partition entries alive at the same time; buffers are freed in a different order than they were made, one
+    matrix outlives its context through DLPack."""
+    import torch
+
+    paths = []
+    for seed in (21, 22):
+        data = synth.generate(n_barcodes=120, mean_pairs=15, read_len=100, n_genomes=3, genome_len=50_000, frag_len=8_000, seed=seed,
+                              unbarcoded_pairs=10, lower_rate=0.001)
+        paths.append(synth.write_interleaved(str(tmp_path / f"b{seed}.fq"), data))
+    table = oracle.count_fastq(paths, 15)
+    want = [oracle.featurize(p, None, table=table) for p in paths]
+    ctx = _ctx()
+    fqs = [_lib.Fastq(p) for p in paths]
+    batches = [ctx.upload(fq.reads) for fq in fqs]
+    for b in batches:
+        ctx.count(b)
+    keys, counts = ctx.table_export()
+    wk, wv = _oracle_table_arrays(table)
+    assert np.array_equal(keys, wk) and np.array_equal(counts.astype(np.uint64), wv)
+    feats = [ctx.featurize(b, fq.group_keep, fq.n_groups) for b, fq in zip(reversed(batches), reversed(fqs))][::-1]
+    batches[0].free()
+    for (names, abd, tnf), f, fq in zip(want, feats, fqs):
+        g_abd, g_tnf = f.raw()
+        assert _names(fq, f) == list(names)
+        assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    t = feats[1].torch(_lib.ABD_RAW)
+    feats[0].free(); feats[1].free(); batches[1].free()
+    ctx.close()
+    assert np.array_equal(t.cpu().numpy(), want[1][1])
+    del t
+    torch.cuda.synchronize()
