@@ -708,22 +708,28 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
         const BucketGeom pg = padded_geom(P.geo);
         const size_t n_seg = (size_t)((n_words + P.seg_words - 1) / P.seg_words);
         const size_t per_seg = (size_t)pg.cap * pg.n_buckets * 4 + (size_t)pg.cap * pg.n_buckets / 32 * 4 + kMaxBuckets * sizeof(unsigned long long);
-        const size_t need = n_seg * per_seg;
-        if (b->min_group_len >= 64 && (packed || !b->nofeat) &&
-            (need <= ctx->ws_stash.bytes || (double)need <= 0.7 * (double)(available_bytes(ctx) + ctx->ws_stash.bytes))) {
+        // as many leading segments as fit (a 125 M-pair batch has 12 of 14.6 GB each): the rest is partitioned per pass
+        // leave room for what this step still allocates (level-2 entries, the scratch partitions of segments that are not
+        // kept, the feature matrices) and 16 GB for the caller
+        const size_t avail = available_bytes(ctx) + ctx->ws_stash.bytes;
+        const size_t reserve = 3 * per_seg + ((size_t)16 << 30);
+        const size_t budget = std::max<size_t>(ctx->ws_stash.bytes, avail > reserve ? (size_t)(0.85 * (double)(avail - reserve)) : 0);
+        size_t n_keep = std::min<size_t>(n_seg, budget / per_seg);
+        if (const char* e = getenv("PG_STASH_SEGMENTS")) n_keep = std::min<size_t>(n_keep, (size_t)std::max(0, atoi(e))); // tests: force a partial stash
+        if (b->min_group_len >= 64 && (packed || !b->nofeat) && n_keep > 0) {
             b->stash_ws = ctx->ws_stash; // borrow the cached buffer (grown if too small)
             ctx->ws_stash = Workspace();
-            if (ws_get(ctx, b->stash_ws, need) == cudaSuccess) {
+            if (ws_get(ctx, b->stash_ws, n_keep * per_seg) == cudaSuccess) {
                 P.shared = true;
                 P.geo = pg;
                 uint8_t* base = (uint8_t*)b->stash_ws.p;
                 const size_t E = (size_t)pg.cap * pg.n_buckets;
-                for (size_t i = 0; i < n_seg; ++i) {
+                for (size_t i = 0; i < n_keep; ++i) {
                     pg_batch::Segment sgm;
                     sgm.w0 = (int64_t)i * P.seg_words; sgm.w1 = std::min<int64_t>(n_words, sgm.w0 + P.seg_words);
                     sgm.entries = (uint32_t*)(base + i * E * 4);
-                    sgm.meta = (int32_t*)(base + n_seg * E * 4 + i * (E / 32) * 4);
-                    sgm.fill = (unsigned long long*)(base + n_seg * E * 4 + n_seg * (E / 32) * 4 + i * kMaxBuckets * sizeof(unsigned long long));
+                    sgm.meta = (int32_t*)(base + n_keep * E * 4 + i * (E / 32) * 4);
+                    sgm.fill = (unsigned long long*)(base + n_keep * E * 4 + n_keep * (E / 32) * 4 + i * kMaxBuckets * sizeof(unsigned long long));
                     sgm.geo = pg;
                     b->stash.push_back(sgm);
                 }
@@ -736,7 +742,9 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
     if (P.shared) {
         e = dmalloc(ctx, &b->stash_lost, 1);
         if (e == cudaSuccess) e = cudaMemsetAsync(b->stash_lost, 0, sizeof(uint32_t), ctx->stream);
-    } else {
+    }
+    const size_t n_seg_all = (size_t)((n_words + P.seg_words - 1) / P.seg_words);
+    if (e == cudaSuccess && (!P.shared || b->stash.size() < n_seg_all)) { // segments that are not kept share one scratch buffer
         e = ws_get(ctx, ctx->ws_entries, (size_t)P.geo.cap * P.geo.n_buckets * 4);
         P.entries = (uint32_t*)ctx->ws_entries.p;
     }
@@ -768,9 +776,9 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
     Q.w0 = w0; Q.w1 = w1;
     FeatParams F = {};
     int rc = PG_OK;
-    if (P.shared) {
-        const size_t si = (size_t)(w0 / P.seg_words);
-        if (si >= b->stash.size() || b->stash[si].w0 != w0 || b->stash[si].w1 != w1) return fail(ctx, PG_ERR_STATE, "count pass: segment does not match the shared partition plan");
+    const size_t si = (size_t)(w0 / P.seg_words);
+    if (P.shared && si < b->stash.size()) {
+        if (b->stash[si].w0 != w0 || b->stash[si].w1 != w1) return fail(ctx, PG_ERR_STATE, "count pass: segment does not match the shared partition plan");
         const pg_batch::Segment& sgm = b->stash[si];
         Q.entries = sgm.entries; Q.meta = sgm.meta; Q.lost = b->stash_lost;
         F.maskF = b->maskR ? b->maskR : b->maskF; F.wg = b->wg; F.gstart = b->gstart; F.n_groups = b->n_groups;
@@ -1134,9 +1142,15 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 CKF(cudaStreamSynchronize(ctx->stream));
                 uint32_t lost = 0;
                 memcpy(&lost, ctx->h_pin, sizeof(lost));
-                int64_t covered = 0;
-                for (auto& sgm : b->stash) covered += sgm.w1 - sgm.w0;
-                reuse = !lost && covered == b->n_words;
+                reuse = !lost;
+            }
+            int64_t covered = 0; // the kept segments are the leading ones
+            if (reuse) {
+                for (auto& sgm : b->stash) {
+                    if (sgm.w0 != covered) { covered = -1; break; }
+                    covered = sgm.w1;
+                }
+                if (covered < 0) { reuse = false; covered = 0; }
             }
             if (reuse) {
                 for (auto& sgm : b->stash) {
@@ -1145,8 +1159,9 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                     Timed t(ctx, T_FEAT, 1);
                     bucket_apply_feat_kernel<true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(sgm.entries, sgm.meta, sgm.geo, ctx->d_bucket, sgm.fill, P);
                 }
-            } else {
-                const int64_t seg_words = std::min<int64_t>(b->n_words, ctx->seg_words);
+            }
+            if (covered < b->n_words) { // what pg_count did not keep (or everything): partition for this pass alone
+                const int64_t seg_words = std::min<int64_t>(b->n_words - covered, ctx->seg_words);
                 const BucketGeom geo = padded_geom(bucket_geom(ctx, seg_words));
                 const size_t E = (size_t)geo.cap * geo.n_buckets;
                 CKF(ws_get(ctx, ctx->ws_feat, E * 4 + E / 32 * 4));
@@ -1155,7 +1170,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 ScatterParams Q = {};
                 Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
                 Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts; Q.lost = nullptr;
-                for (int64_t w0 = 0; w0 < b->n_words; w0 += seg_words) {
+                for (int64_t w0 = covered; w0 < b->n_words; w0 += seg_words) {
                     Q.w0 = w0; Q.w1 = std::min(b->n_words, w0 + seg_words);
                     {
                         Timed t(ctx, T_FEAT_SCATTER, 2);

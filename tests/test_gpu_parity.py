@@ -138,7 +138,8 @@ def test_tiny_clouds_overflow_the_slots(tmp_path, oracle):
 @pytest.mark.parametrize("env", [{}, {"PG_SEG_WORDS": "512"}, {"PG_FORCE_DIRECT": "1"}, {"PG_REGION_SLACK": "0.3"},
                                  {"PG_REGION_SLACK": "0.02", "PG_SEG_WORDS": "2048"}, {"PG_COUNT_L2": "1"},
                                  {"PG_COUNT_L2": "1", "PG_REGION_SLACK": "0.3"}, {"PG_COUNT_L2": "1", "PG_SEG_WORDS": "1024"},
-                                 {"PG_NO_SHARED": "1"}, {"PG_NO_SHARED": "1", "PG_SEG_WORDS": "1024"}, {"PG_NO_SHARED": "1", "PG_REGION_SLACK": "0.3"}])
+                                 {"PG_NO_SHARED": "1"}, {"PG_NO_SHARED": "1", "PG_SEG_WORDS": "1024"}, {"PG_NO_SHARED": "1", "PG_REGION_SLACK": "0.3"},
+                                 {"PG_SEG_WORDS": "1024", "PG_STASH_SEGMENTS": "3"}, {"PG_SEG_WORDS": "2048", "PG_STASH_SEGMENTS": "1", "PG_COUNT_L2": "1"}])
 def test_sliced_and_direct_table_paths_agree(tmp_path, oracle, monkeypatch, env):
     """k = 15 uses the L2-sliced path (bucket.cuh) by default; PG_SEG_WORDS forces many
     segments on a small input, PG_FORCE_DIRECT the one-kernel path, PG_REGION_SLACK < 1 makes
@@ -146,7 +147,8 @@ def test_sliced_and_direct_table_paths_agree(tmp_path, oracle, monkeypatch, env)
     scatter / split kernels, PG_COUNT_L2 applies the count entries with L2 atomics instead of the
     shared-memory sub-slices (count2.cuh), PG_NO_SHARED partitions separately for the count and the
     featurize pass instead of once for both (the default when clouds are >= 64 bytes; an overflow there
-    makes pg_featurize fall back to its own partition).  All must equal the oracle."""
+    makes pg_featurize fall back to its own partition), PG_STASH_SEGMENTS keeps only the first segments of the shared
+    partition (what a batch too large for HBM gets).  All must equal the oracle."""
     for k_, v in env.items():
         monkeypatch.setenv(k_, v)
     data = synth.generate(n_barcodes=150, mean_pairs=14, read_len=100, n_genomes=3, genome_len=60_000, frag_len=8_000,
