@@ -307,10 +307,8 @@ def main():
         ctx.table_clear(); mark("clear")
         b = ctx.adopt(batch_data["reads"]); mark("adopt+pack")
         ctx.count(b); mark("count")
-        if world > 1:  # the one exchange step of the path: sum the dense count tables
-            ctx.synchronize()
-            dist.all_reduce(table_t)
-            torch.cuda.synchronize()
+        if world > 1:  # the one exchange step of the path: sum the dense count tables (overlaps grouping + TNF of featurize)
+            ctx.all_reduce_table(table_t)
         f = ctx.featurize(b, keep); mark("featurize")
         f.normalize(); mark("normalize")
         b.free(); mark("free")
@@ -442,9 +440,7 @@ def run_e2e(args, ctx, batch_data, keep, rows, world, local_rank, barrier, table
             ctx.table_clear()
             b = ctx.upload(reads)
             ctx.count(b)
-            ctx.synchronize()
-            dist.all_reduce(table_t)
-            torch.cuda.synchronize()
+            ctx.all_reduce_table(table_t)
             f = ctx.featurize(b, keep)
             b.free()
         f.normalized(h_abd, h_tnf, h_w)

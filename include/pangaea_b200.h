@@ -120,6 +120,10 @@ int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts_out, int64
 /* dense mode only: device pointer and entry count of the u32 counter array, so a
  * data-parallel caller can sum tables across ranks (ncclAllReduce) - SURVEY §8e */
 int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entries);
+/* the caller is still writing the table on another stream (the all-reduce): every later launch of this ctx that reads
+ * or writes the table first waits for `cuda_event` (a cudaEvent_t recorded after that work).  The parts of
+ * pg_featurize that do not need the table (cloud grouping, TNF) run ahead of it - they overlap the collective. */
+int pg_table_wait_event(pg_ctx* ctx, void* cuda_event);
 
 /* ---- step 1b: per-cloud abundance histogram + TNF --------------------------- */
 /* replaces bin/count_kmer (countKmer, count_kmer.cpp:55-108) and bin/count_tnf

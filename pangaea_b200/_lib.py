@@ -63,6 +63,7 @@ SIGNATURES = {
     "pg_table_size": (_int, [_vp, _P(_i64)]),
     "pg_table_export": (_int, [_vp, _vp, _vp, _i64, _P(_i64)]),
     "pg_table_dense_view": (_int, [_vp, _P(_vp), _P(_i64)]),
+    "pg_table_wait_event": (_int, [_vp, _vp]),
     "pg_featurize": (_int, [_vp, _vp, _vp, _i64, _P(_vp)]),
     "pg_features_free": (None, [_vp, _vp]),
     "pg_features_rows": (_i64, [_vp]),
@@ -314,6 +315,33 @@ class Context:
         p, n = _vp(), _i64()
         self._ck(lib().pg_table_dense_view(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def table_wait_event(self, cuda_event: int):
+        """Later table readers of this ctx wait for the CUDA event (raw cudaEvent_t, e.g. torch.cuda.Event.cuda_event)."""
+        self._ck(lib().pg_table_wait_event(self.h, C.c_void_p(int(cuda_event))))
+
+    def all_reduce_table(self, table_t, group=None):
+        """Sum the dense count tables across ranks (NCCL) WITHOUT stalling this ctx: the collective runs on a side stream
+        ordered after the count kernels, and only the kernels that read the table wait for it - cloud grouping and the TNF
+        kernel of the next pg_featurize overlap the all-reduce.  Keep the returned objects alive until that call returns."""
+        import torch
+        import torch.distributed as dist
+
+        dev = f"cuda:{self.params.device}"
+        counted = torch.cuda.Event()
+        with torch.cuda.stream(torch.cuda.ExternalStream(self.stream, device=dev)):
+            counted.record()
+        side = getattr(self, "_side_stream", None) or torch.cuda.Stream(device=dev)
+        self._side_stream = side
+        side.wait_event(counted)
+        with torch.cuda.stream(side):
+            work = dist.all_reduce(table_t, group=group, async_op=True)
+            work.wait()  # orders `side` after NCCL's stream; does not block the host
+            done = torch.cuda.Event()
+            done.record(side)
+        self.table_wait_event(done.cuda_event)
+        self._pending_reduce = (work, done, counted)
+        return self._pending_reduce
 
     def table_as_torch(self):
         """The dense counter array as an int32 CUDA tensor sharing memory (for all_reduce)."""

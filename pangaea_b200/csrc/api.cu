@@ -63,6 +63,7 @@ struct pg_ctx {
     uint64_t n_slots = 0;
     uint32_t* d_overflow = nullptr;
     bool counted = false;
+    cudaEvent_t table_event = nullptr; // pending external write to the table (pg_table_wait_event); not owned
     // TNF look-up table
     uint16_t* d_lut = nullptr;
     // pinned read-back scratch
@@ -583,10 +584,13 @@ extern "C" void pg_batch_free(pg_ctx* ctx, pg_batch* b)
 // ---------------------------------------------------------------------------
 // table
 // ---------------------------------------------------------------------------
+static int table_ready(pg_ctx* ctx);
+
 extern "C" int pg_table_clear(pg_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     if (ctx->counts) CK(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
     if (ctx->keys) CK(cudaMemsetAsync(ctx->keys, 0xFF, ctx->n_slots * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(uint32_t), ctx->stream));
@@ -711,10 +715,14 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
         // as many leading segments as fit (a 125 M-pair batch has 12 of 14.6 GB each): the rest is partitioned per pass
         // leave room for what this step still allocates (level-2 entries, the scratch partitions of segments that are not
         // kept, the feature matrices) and 16 GB for the caller
-        const size_t avail = available_bytes(ctx) + ctx->ws_stash.bytes;
-        const size_t reserve = 3 * per_seg + ((size_t)16 << 30);
-        const size_t budget = std::max<size_t>(ctx->ws_stash.bytes, avail > reserve ? (size_t)(0.85 * (double)(avail - reserve)) : 0);
-        size_t n_keep = std::min<size_t>(n_seg, budget / per_seg);
+        size_t n_keep = n_seg;
+        if (n_seg * per_seg > ctx->ws_stash.bytes) { // the cached buffer is too small: how much may it grow?  (steady-state
+            // steps never get here - the memory queries below were seen to stall a step for tens of ms on a fresh box)
+            const size_t avail = available_bytes(ctx) + ctx->ws_stash.bytes;
+            const size_t reserve = 3 * per_seg + ((size_t)16 << 30);
+            const size_t budget = std::max<size_t>(ctx->ws_stash.bytes, avail > reserve ? (size_t)(0.85 * (double)(avail - reserve)) : 0);
+            n_keep = std::min<size_t>(n_seg, budget / per_seg);
+        }
         if (const char* e = getenv("PG_STASH_SEGMENTS")) n_keep = std::min<size_t>(n_keep, (size_t)std::max(0, atoi(e))); // tests: force a partial stash
         if (b->min_group_len >= 64 && (packed || !b->nofeat) && n_keep > 0) {
             b->stash_ws = ctx->ws_stash; // borrow the cached buffer (grown if too small)
@@ -823,6 +831,7 @@ extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
 {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     int rc = ensure_table(ctx, b->n_bytes);
     if (rc) return rc;
     if (b->n_words && use_buckets(ctx)) {
@@ -843,6 +852,7 @@ extern "C" int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* c
 {
     if (!ctx || (n > 0 && (!keys || !counts)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_set: bad argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     int rc = ensure_table(ctx, n);
     if (rc) return rc;
     ctx->counted = true;
@@ -880,6 +890,7 @@ extern "C" int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* out, in
     if (!ctx || (n > 0 && (!keys || !out)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_get: bad argument");
     if (!n) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     if (!ctx->counts) { memset(out, 0, (size_t)n * sizeof(uint32_t)); return PG_OK; }
     uint64_t* dk; uint32_t* dc;
     CK(dmalloc(ctx, &dk, (size_t)n)); CK(dmalloc(ctx, &dc, (size_t)n));
@@ -898,6 +909,7 @@ extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
     *n_distinct = 0;
     if (!ctx->counts) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
     table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, (unsigned long long*)ctx->d_scalar);
     CK(cudaGetLastError());
@@ -913,6 +925,7 @@ extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts
     *n_out = 0;
     if (!ctx->counts || !cap) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     uint64_t* dk; uint32_t* dc;
     CK(dmalloc(ctx, &dk, (size_t)cap)); CK(dmalloc(ctx, &dc, (size_t)cap));
     CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
@@ -933,6 +946,24 @@ extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts
     for (int64_t i = 0; i < n; ++i) { keys_out[i] = hk[order[i]]; counts_out[i] = hc[order[i]]; }
     *n_out = n;
     if (ctx->h_pin[0] > cap) return fail(ctx, PG_ERR_INVALID, "pg_table_export: buffer too small");
+    return PG_OK;
+}
+
+// order the ctx stream after a pending external write of the table; called by everything that touches the table
+static int table_ready(pg_ctx* ctx)
+{
+    if (ctx->table_event) {
+        cudaEvent_t ev = ctx->table_event;
+        ctx->table_event = nullptr;
+        CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_table_wait_event(pg_ctx* ctx, void* cuda_event)
+{
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    ctx->table_event = (cudaEvent_t)cuda_event;
     return PG_OK;
 }
 
@@ -1135,6 +1166,8 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 if (P.tnf_k == 4) tnf_kernel<4><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
                 else tnf_kernel<0><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
             }
+            rc = table_ready(ctx); // the table may still be inside an all-reduce: grouping and TNF above did not need it
+            if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
             // entries kept by pg_count (shared partition)?  usable unless an overflow path bypassed the buffer
             bool reuse = !b->stash.empty() && b->stash_lost;
             if (reuse) {
@@ -1186,6 +1219,8 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
             *out = f;
             return PG_OK;
         }
+        rc = table_ready(ctx);
+        if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
         const size_t smem = (size_t)kSlots * (P.vs + P.td) * sizeof(uint32_t) + ((size_t)2 << (2 * P.tnf_k));
         int occ = 1;
         if (ctx->mode == kDense) CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, featurize_kernel<kDense>, kFeatThreads, smem));

@@ -35,9 +35,8 @@ def extract_features_sharded(ctx: "_lib.Context", seq, read_off, read_flag, grou
     batch = ctx.upload(reads)
     ctx.count(batch)
     if world > 1:
-        table = ctx.table_as_torch()          # synchronises the ctx stream
-        dist.all_reduce(table, group=group)   # NCCL over NVLink / NVSwitch
-        torch.cuda.synchronize()
+        table = ctx.table_as_torch()
+        ctx.all_reduce_table(table, group=group)  # NCCL over NVLink / NVSwitch, overlapped with grouping + TNF below
     feats = ctx.featurize(batch, keep)
     feats.normalize()
     batch.free()
