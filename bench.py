@@ -95,6 +95,62 @@ def write_sample_fastq(path, seq_host, read_len, bc_start, n_pairs):
                 f.write(h + bytes(mv[o:o + read_len]) + b"\n+\n" + q + b"\n")
 
 
+def write_sample_fastq_fast(path, seq_host, read_len, bc_start, n_pairs):
+    """Same file as write_sample_fastq, built with numpy (fixed-width read ids) - for the larger ingest sample."""
+    rl = read_len + 1
+    bc_of_pair = (np.searchsorted(bc_start, np.arange(n_pairs), side="right") - 1).astype(np.int64)
+    bc_of_read = np.repeat(bc_of_pair, 2)
+    ids = np.repeat(np.arange(n_pairs, dtype=np.int64), 2)
+    n = 2 * n_pairs
+    hdr = np.zeros((n, 2 + 10 + 6 + 16 + 3), dtype=np.uint8)
+    hdr[:, 0:2] = np.frombuffer(b"@r", dtype=np.uint8)
+    for d in range(10):
+        hdr[:, 2 + d] = ord("0") + (ids // 10 ** (9 - d)) % 10
+    hdr[:, 12:18] = np.frombuffer(b"\tBX:Z:", dtype=np.uint8)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for i in range(16):
+        hdr[:, 18 + i] = letters[(bc_of_read >> (2 * (15 - i))) & 3]
+    hdr[:, 34:37] = np.frombuffer(b"-1\n", dtype=np.uint8)
+    rec = np.empty((n, hdr.shape[1] + rl + 2 + rl), dtype=np.uint8)
+    rec[:, :hdr.shape[1]] = hdr
+    o = hdr.shape[1]
+    rec[:, o:o + read_len] = np.asarray(seq_host[: n * rl]).reshape(n, rl)[:, :read_len]
+    rec[:, o + read_len] = ord("\n")
+    rec[:, o + rl:o + rl + 2] = np.frombuffer(b"+\n", dtype=np.uint8)
+    rec[:, o + rl + 2:o + rl + 2 + read_len] = ord("I")
+    rec[:, -1] = ord("\n")
+    rec.tofile(path)
+
+
+def ingest_from_fastq(args, ctx, batch_data, n_pairs=2_000_000):
+    """The drop-in call a Pangaea user makes: a barcode-sorted interleaved FASTQ on disk -> feature matrices on the host
+    (pg_fastq_parse with all host cores + pg_extract_features + copy back), on the first n_pairs pairs of the batch."""
+    from pangaea_b200 import _lib
+
+    n = min(n_pairs, batch_data["n_pairs"])
+    rl = batch_data["read_len"] + 1
+    host = batch_data["seq"][: 2 * n * rl].cpu().numpy()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "sample.fq")
+        write_sample_fastq_fast(path, host, batch_data["read_len"], batch_data["bc_start"], n)
+        size = os.path.getsize(path)
+        best = None
+        for _ in range(3):  # first pass warms the page cache and the ctx workspaces
+            t0 = time.perf_counter()
+            fq = _lib.Fastq(path)
+            t1 = time.perf_counter()
+            f = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+            f.normalized()
+            t2 = time.perf_counter()
+            rows = f.rows
+            f.free(); fq.close()
+            if best is None or t2 - t0 < best[0]:
+                best = (t2 - t0, t1 - t0, t2 - t1)
+    return {"value": round(2 * n / best[0], 1), "unit": UNIT, "parse_s": round(best[1], 3), "gpu_and_copies_s": round(best[2], 3),
+            "file_GB": round(size / 1e9, 3), "parse_GBps": round(size / 1e9 / best[1], 2), "host_threads": os.cpu_count(), "rows": rows,
+            "sample": f"first {n} pairs of the batch as a plain-text interleaved FASTQ on local disk (page cache), best of 3"}
+
+
 # --------------------------------------------------------------------------------------
 # CPU reference arm: jellyfish stand-in + oracle/_ref/count_kmer ‖ oracle/_ref/count_tnf
 # --------------------------------------------------------------------------------------
@@ -405,6 +461,10 @@ def main():
     if e2e:
         out["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["from_fastq"] = ingest_from_fastq(args, ctx, batch_data)
+        except Exception as e:  # informational: never lose the bench line over it
+            out["from_fastq"] = {"value": None, "error": str(e)[:200]}
         out["cpu_baseline"] = cpu_baseline_from_batch(args, batch_data)
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -508,3 +508,33 @@ def test_two_batches_one_table(tmp_path, oracle):
     assert np.array_equal(t.cpu().numpy(), want[1][1])
     del t
     torch.cuda.synchronize()
+
+
+def test_pipelined_upload_with_unpaired_reads_and_lower_case(tmp_path, oracle):
+    """pg_extract_features on > 1 MB goes through the chunked upload (the count pass runs while later chunks are still
+    crossing PCIe).  Paired files with mismatching R1/R2 names (counted, but in no cloud: PG_READ_NOFEAT) and lower-case
+    bases (counted, not featurized) exercise the count-only windows on that path."""
+    data = synth.generate(n_barcodes=500, mean_pairs=12, read_len=100, n_genomes=4, genome_len=100_000, frag_len=10_000, seed=31,
+                          unbarcoded_pairs=50, lower_rate=0.002)
+    p1, p2 = synth.write_paired(str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq"), data)
+    lines = open(p2, "rb").read().split(b"\n")
+    for i in range(0, len(lines) - 4, 4 * 37):  # every 37th R2 record gets another name
+        lines[i] = b"@other" + lines[i][1:]
+    open(p2, "wb").write(b"\n".join(lines))
+    names, abd, tnf = oracle.featurize(p1, p2)
+    fq = _lib.Fastq(p1, p2)
+    assert fq.reads.n_bytes > (1 << 20) and (fq.arrays()[2] & _lib.PG_READ_NOFEAT).any()
+    for seg in (None, "8192"):  # one chunk / many chunks
+        if seg:
+            os.environ["PG_SEG_WORDS"] = seg
+        try:
+            ctx = _ctx()
+            feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
+            g_abd, g_tnf = feats.raw()
+            assert _names(fq, feats) == list(names)
+            assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+            keys, counts = ctx.table_export()
+            wk, wv = _oracle_table_arrays(oracle.count_fastq([p1, p2], 15))
+            assert np.array_equal(keys, wk) and np.array_equal(counts.astype(np.uint64), wv)
+        finally:
+            os.environ.pop("PG_SEG_WORDS", None)
