@@ -75,6 +75,8 @@ struct pg_ctx {
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
+    int tnf_overlap = 2;         // PG_TNF_OVERLAP=n: the TNF kernel runs on the second stream with n CTAs per SM, next to the look-up
+                                 // sweep (0 = in line on the ctx stream)
     bool no_shared = false;      // PG_NO_SHARED=1: separate partitions for the count and featurize passes (A/B, tests)
     bool count_l2 = false;       // PG_COUNT_L2=1: apply the count entries with L2 atomics instead of the shared-memory sub-slices (A/B)
     int64_t count_seg_words = 1ll << 26; // segment of the count pass (2^31 windows: 13 GB of u32 + 6 GB of u16 entries); PG_SEG_WORDS overrides
@@ -139,22 +141,22 @@ static int fail(pg_ctx* c, int code, const std::string& msg)
             return fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
 
-struct Timed { // CUDA-event span on the ctx stream around the launches of one stage
-    pg_ctx* c; int which; cudaEvent_t a = nullptr, b = nullptr;
+struct Timed { // CUDA-event span around the launches of one stage, on the ctx stream unless told otherwise
+    pg_ctx* c; int which; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t on = nullptr;
     static cudaEvent_t get(pg_ctx* c)
     {
         if (!c->pool.empty()) { cudaEvent_t e = c->pool.back(); c->pool.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
-    Timed(pg_ctx* c_, int w, int n_launches) : c(c_), which(w)
+    Timed(pg_ctx* c_, int w, int n_launches, cudaStream_t on_ = nullptr) : c(c_), which(w), on(on_ ? on_ : c_->stream)
     {
         a = get(c); b = get(c);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, on);
         c->launches[w] += n_launches;
     }
     ~Timed()
     {
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, on);
         c->spans.push_back({ which, a, b });
         if (c->spans.size() > 4096) { // nobody is reading the spans: recycle the oldest
             c->pool.push_back(c->spans.front().a); c->pool.push_back(c->spans.front().b);
@@ -356,6 +358,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = ctx->count_seg_words = atoll(e) / 512 * 512; }
     { const char* e = getenv("PG_COUNT_L2"); ctx->count_l2 = e && e[0] == '1'; }
     { const char* e = getenv("PG_NO_SHARED"); ctx->no_shared = e && e[0] == '1'; }
+    { const char* e = getenv("PG_TNF_OVERLAP"); if (e) ctx->tnf_overlap = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("PG_FEAT_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
     if (ctx->mode == kDense) {
@@ -1076,7 +1079,9 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     int rc = PG_OK;
     pg_features* f = nullptr;
     const bool sliced = use_buckets(ctx);
+    cudaEvent_t tnf_fork = nullptr, tnf_join = nullptr; // TNF kernel on the second stream (sliced path)
     auto cleanup = [&]() {
+        if (tnf_join) { cudaStreamWaitEvent(ctx->stream, tnf_join, 0); ctx->pool.push_back(tnf_fork); ctx->pool.push_back(tnf_join); tnf_fork = tnf_join = nullptr; }
         dfree(ctx, d_keep); dfree(ctx, emit);
         dfree(ctx, row_of_group); dfree(ctx, group_of_row_full);
         dfree(ctx, row_lb);
@@ -1156,15 +1161,28 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
                 P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
                 const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb;
-                const int64_t max_cta = (int64_t)ctx->sm_count * 8;
+                // The TNF kernel is bound by shared-memory atomics, the look-up sweep below by L1 gathers: with a few CTAs per SM
+                // on the second stream it runs NEXT TO the sweep instead of before it.
+                const bool side = ctx->tnf_overlap > 0;
+                const int64_t max_cta = (int64_t)ctx->sm_count * (side ? ctx->tnf_overlap : 8);
                 const int64_t n_cta = std::min<int64_t>(max_cta, (b->n_words + kTnfThreads - 1) / kTnfThreads);
                 int64_t wpc = (b->n_words + n_cta - 1) / n_cta;
                 wpc = (wpc + kTnfThreads - 1) / kTnfThreads * kTnfThreads;
                 P.words_per_cta = wpc;
                 const int grid = (int)((b->n_words + wpc - 1) / wpc);
-                Timed t(ctx, T_TNF, 1);
-                if (P.tnf_k == 4) tnf_kernel<4><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
-                else tnf_kernel<0><<<grid, kTnfThreads, smem_t, ctx->stream>>>(P);
+                cudaStream_t ts = ctx->stream;
+                if (side) {
+                    ts = ctx->copy_stream;
+                    tnf_fork = Timed::get(ctx); tnf_join = Timed::get(ctx);
+                    CKF(cudaEventRecord(tnf_fork, ctx->stream)); // grouping, the cleared matrices
+                    CKF(cudaStreamWaitEvent(ts, tnf_fork, 0));
+                }
+                {
+                    Timed t(ctx, T_TNF, 1, ts);
+                    if (P.tnf_k == 4) tnf_kernel<4><<<grid, kTnfThreads, smem_t, ts>>>(P);
+                    else tnf_kernel<0><<<grid, kTnfThreads, smem_t, ts>>>(P);
+                }
+                if (side) CKF(cudaEventRecord(tnf_join, ts));
             }
             rc = table_ready(ctx); // the table may still be inside an all-reduce: grouping and TNF above did not need it
             if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
