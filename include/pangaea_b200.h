@@ -106,7 +106,10 @@ int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE fl
 
 /* ---- step 1a: global canonical k-mer counts --------------------------------- */
 /* replaces `jellyfish count -C -m k` (+ `dump`), feature.py:76-94,103, and the dump
- * loader count_kmer.cpp:139-170 (the table simply stays in HBM).  Adds the batch. */
+ * loader count_kmer.cpp:139-170 (the table simply stays in HBM).  Adds the batch.
+ * Dense mode, k <= 15: the partition of the k-mer windows by table slice that this pass computes is the one
+ * pg_featurize needs too, so - memory permitting - it is KEPT in the batch (about 0.75 KB per read pair of 2x100 bp,
+ * from a buffer the ctx reuses) until pg_batch_free; pg_featurize of the same batch then skips its own partition. */
 int pg_count(pg_ctx* ctx, pg_batch* b);
 int pg_table_clear(pg_ctx* ctx);
 /* kmer2frequency[key] = count (count_kmer.cpp:166): assignment, keys in the reference's

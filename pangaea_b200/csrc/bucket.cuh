@@ -23,14 +23,17 @@
 //   * a region (pathological repeats) - the run is applied straight from the staging row.
 // The stream is processed in segments so the entry buffer stays bounded.
 //
-// Entry (u32), from y = 8 * (scrambled class id): bits 3..25 = index inside the slice.
-//   count   : the whole y (top 6 bits = slice, low 3 bits zero).
-//   feature : top 6 + low 3 bits carry the row as a 9-bit delta against the tile's base row;
-//             runs are padded to a multiple of 32 entries with kInvalidEntry and every aligned
-//             group of 32 entries has its base row in a side array (4 B per 128 B of
-//             entries).  The apply pass gathers the count (L2 hit), bins it
-//             (count_kmer.cpp:90-93) and reduces equal (row, bin) pairs inside the warp before
-//             one RED into the abundance matrix.
+// Entry (u32), from y = 8 * (scrambled class id): bits 3..25 = index inside the slice; the other 9 bits (top 6 + low 3)
+// depend on the kind of partition (kScatter* below):
+//   shared  : ONE partition serves both passes (the default).  The 9 bits are the window's cloud as a delta against the
+//             first cloud of the tile (510 = window that is counted but not featurized, 511 = padding).  Runs are padded
+//             to a multiple of 32 entries with kInvalidEntry and every aligned group of 32 entries has its base cloud in
+//             a side array (4 B per 128 B of entries).  pg_count keeps the buffer; pg_featurize sweeps it again.
+//   count   : entries for the count pass alone: the whole y (top 6 bits = slice, low 3 bits zero), runs padded to 4.
+//   feature : entries for the featurize pass alone: as shared, but the delta is a ROW delta (rows are known by then).
+// The count pass partitions its entries once more (count2.cuh); the featurize apply gathers the count (L2 hit), bins it
+// (count_kmer.cpp:90-93), maps cloud -> row and reduces equal (row, bin) pairs inside the warp before one RED into the
+// abundance matrix.
 #pragma once
 #include "featurize.cuh"
 #include "scan.cuh"

@@ -1,4 +1,6 @@
-// featurize.cuh - step 1b: per-cloud abundance histogram + TNF in ONE pass.
+// featurize.cuh - step 1b: per-cloud abundance histogram + TNF in ONE pass - the DIRECT path (hash table for k > 16,
+// k = 16, tiny tables, PG_FORCE_DIRECT); for k <= 15 the sliced path of bucket.cuh / tnf.cuh is about 5x faster.
+// FeatParams and the small helpers below are shared with that path.
 //
 // Replaces bin/count_kmer's countKmer (src/cpptools/count_kmer.cpp:55-108: rolling
 // canonical k-mer -> global count c -> ++hist[c / w] if c / w < v; k-mers absent
