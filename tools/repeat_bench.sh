@@ -4,4 +4,4 @@ for i in 1 2 3 4; do
 import json
 d=json.loads(open('gpurun_out/rep_$i.log').read().strip().splitlines()[-1]); print($i, d['value'], d['ms_per_step'], d['device_ms_per_step'], sum(d['roofline']['stages_ms'].values()), d['roofline']['stages_ms']['feat_apply'])
 PY
-done
+done 2>/dev/null
