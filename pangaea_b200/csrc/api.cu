@@ -1001,12 +1001,13 @@ static int scan_flags(pg_ctx* ctx, const uint8_t* d_flags, int64_t n, uint32_t b
 
 extern "C" int64_t pg_batch_n_groups(const pg_batch* b) { return b ? b->n_groups : -1; }
 
-// smallest cloud of the batch, in bytes (0 when some cloud is empty)
+// smallest cloud of the batch, in bytes.  A cloud holds at least the read that carries its PG_READ_CHANGE flag; only the
+// LAST one (what follows the last flag) can be empty - it owns no base and is skipped here.
 __global__ void min_group_len_kernel(const int64_t* __restrict__ gstart, int64_t n_groups, unsigned long long* __restrict__ out)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long len = ~0ull;
-    if (g < n_groups) len = (unsigned long long)(gstart[g + 1] - gstart[g]);
+    if (g < n_groups && gstart[g + 1] > gstart[g]) len = (unsigned long long)(gstart[g + 1] - gstart[g]);
 #pragma unroll
     for (int d = 16; d; d >>= 1) len = min(len, __shfl_xor_sync(0xffffffffu, len, d));
     if ((threadIdx.x & 31) == 0 && len != ~0ull) atomicMin(out, len);
