@@ -350,10 +350,19 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             // from the own lane is the identity, but not one the optimiser can see through (2 SHFL per 32 windows)
             lo = __shfl_sync(__activemask(), lo, lane);
             hi = __shfl_sync(__activemask(), hi, lane);
+            // four windows at a time: the four returning atomics are issued back to back, so their latency overlaps
+            uint32_t yb[4];
             for_each_window<KT>(lo, hi, k, [&](int i, uint32_t y) {
-                const uint32_t b = (v & (1u << i)) ? (y >> 26) : (uint32_t)kMaxBuckets;
-                const uint32_t slot = min(atomicAdd(cnt + b, 1u), (uint32_t)(CAP - 1)); // a row that overflows is redone below
-                stage[b * STRIDE + slot] = FEAT ? ((y & kEntryIndexBits) | d) : y;
+                yb[i & 3] = y;
+                if ((i & 3) != 3) return;
+                uint32_t bk[4], slot[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bk[q] = (v & (1u << (i - 3 + q))) ? (yb[q] >> 26) : (uint32_t)kMaxBuckets;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) slot[q] = atomicAdd(cnt + bk[q], 1u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) // a row that overflows is redone below
+                    stage[bk[q] * STRIDE + min(slot[q], (uint32_t)(CAP - 1))] = FEAT ? ((yb[q] & kEntryIndexBits) | d) : yb[q];
             });
         }
         __syncthreads();

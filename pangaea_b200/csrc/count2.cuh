@@ -104,12 +104,13 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
         for (int u = 0; u < kSplitPer / 4; ++u) {
             const uint32_t i0 = 4u * (u * kSplitThreads + threadIdx.x);
             const uint32_t v[4] = { e[u].x, e[u].y, e[u].z, e[u].w };
+            uint32_t sub[4], slot[4]; // the four returning atomics back to back: their latency overlaps
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t sub = (i0 + c < n && v[c] != kInvalidEntry) ? ((v[c] >> (3 + kSubBits)) & (kSubFan - 1)) : (uint32_t)kSubFan;
-                const uint32_t slot = min(atomicAdd(cnt + sub, 1u), (uint32_t)(kSplitCap - 1));
-                stage[sub * kSplitStride + slot] = (uint16_t)((v[c] >> 3) & (kSubWords - 1));
-            }
+            for (int c = 0; c < 4; ++c) sub[c] = (i0 + c < n && v[c] != kInvalidEntry) ? ((v[c] >> (3 + kSubBits)) & (kSubFan - 1)) : (uint32_t)kSubFan;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) slot[c] = atomicAdd(cnt + sub[c], 1u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) stage[sub[c] * kSplitStride + min(slot[c], (uint32_t)(kSplitCap - 1))] = (uint16_t)((v[c] >> 3) & (kSubWords - 1));
         }
         __syncthreads();
         if (threadIdx.x < kSubFan) { // claim one run per sub-region
