@@ -30,6 +30,20 @@ def _reference_text_rounding(m: np.ndarray) -> np.ndarray:
     return out
 
 
+def write_reference_csv(path, names, matrix):
+    """The gz-CSV artefact the reference tools leave next to the pickles (count_kmer.cpp:202-215, count_tnf.cpp:195-208):
+    one line ``label,v0,v1,...`` per cloud, values printed like ``ostream << double`` at the default precision 6
+    (integers below 10^6 as integers, larger ones as ``1.11493e+06``).  Optional: nothing downstream of the pickles reads it."""
+    import gzip
+
+    m = np.asarray(matrix)
+    small = (m < 1_000_000).all()
+    with gzip.open(path, "wt", compresslevel=1, newline="\n") as f:
+        for name, row in zip(names, m):
+            vals = [str(int(v)) for v in row] if small else ["%g" % float(v) for v in row]
+            f.write(str(name) + "," + ",".join(vals) + "\n")
+
+
 class Feature:
     def __init__(self, args, script_path=None, device=0):
         # /root/reference/src/feature.py:12-26
@@ -62,7 +76,13 @@ class Feature:
             return a.interleaved_reads, None, 0
         raise ValueError("reads must be specified")  # feature.py:99,111,135
 
-    def extract_features(self, write_cache=True, reference_text_rounding=True):
+    def _abd_csv(self):
+        return os.path.join(self.feature_dir, f"abundance.k{self.kmer}.v{self.vs}.w{self.ws}.m{self.minl}.gz")
+
+    def _tnf_csv(self):
+        return os.path.join(self.feature_dir, f"tnf.m{self.minl}.gz")
+
+    def extract_features(self, write_cache=True, reference_text_rounding=True, write_csv=False):
         """-> (names[G] object, abundance[G, v], tnf[G, 136]) in file order (feature.py:28-39)."""
         import pandas as pd
 
@@ -89,6 +109,9 @@ class Feature:
                     df.columns = range(1, m.shape[1] + 1)
                     df.insert(0, 0, names)
                     df.to_pickle(path)
+            if write_csv:  # the intermediate text files of the reference (feature.py:104-109,128-135); raw tallies
+                write_reference_csv(self._abd_csv(), names, abd32)
+                write_reference_csv(self._tnf_csv(), names, tnf32)
         logging.info(f"abundance shape {abundance.shape}")
         logging.info(f"tnf shape {tnf.shape}")
         with open(os.path.join(self.feature_dir, "feature_finished"), "w") as f:

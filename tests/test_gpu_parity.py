@@ -325,12 +325,16 @@ def test_feature_and_data_drop_in(tmp_path, oracle):
     path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
     names, abd, tnf = oracle.featurize(path, None)
     ft = Feature(_args(tmp_path, interleaved_reads=path), script_path="unused")
-    g_names, g_abd, g_tnf = ft.extract_features()
+    g_names, g_abd, g_tnf = ft.extract_features(write_csv=True)
     assert g_abd.dtype == np.int64 and g_abd.shape == abd.shape
     assert list(g_names) == list(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
     fd = tmp_path / "1.features"
     assert (fd / "feature_finished").read_text() == "feature finished"
     assert (fd / "abundance.k15.v400.w10.m2000.pkl").exists() and (fd / "tnf.m2000.pkl").exists()
+    import pandas as pd  # the optional text artefacts parse the way the reference parses its own (feature.py:115,139)
+    for csv, want in ((fd / "abundance.k15.v400.w10.m2000.gz", abd), (fd / "tnf.m2000.gz", tnf)):
+        df = pd.read_csv(csv, header=None)
+        assert list(df[0]) == list(names) and np.array_equal(df.drop(columns=0).to_numpy(), want)
     l_names, l_abd, l_tnf = Feature(_args(tmp_path, interleaved_reads=path), "unused").load_features()
     assert list(l_names) == list(names) and np.array_equal(l_abd, abd) and np.array_equal(l_tnf, tnf)
 

@@ -139,3 +139,20 @@ def test_parallel_reader_equals_sequential_reader(tmp_path, monkeypatch, threads
         for a, b in zip(want[:4], got[:4]):
             assert np.array_equal(a, b), path
         assert want[4] == got[4] and want[5] == got[5], path
+
+
+def test_reference_csv_writer_matches_the_reference_tools(tmp_path, golden):
+    """Feature(write_csv=True) leaves the same text the reference binaries wrote (golden abundance.csv / tnf.csv), including
+    the precision-6 scientific notation of tallies >= 10^6 (KAT-5)."""
+    import gzip
+
+    from pangaea_b200.feature import write_reference_csv
+
+    for labels, m, name in ((golden.abd_labels, golden.abd, "abundance.csv"), (golden.tnf_labels, golden.tnf, "tnf.csv")):
+        out = tmp_path / (name + ".gz")
+        write_reference_csv(str(out), labels, m)
+        want = open(os.path.join(golden.dir, name)).read()
+        assert gzip.open(out, "rt").read() == want
+    big = np.array([[1114930, 3, 999999, 1000000, 12345678]])
+    write_reference_csv(str(tmp_path / "big.gz"), ["AC"], big)
+    assert gzip.open(tmp_path / "big.gz", "rt").read() == "AC,1.11493e+06,3,999999,1e+06,1.23457e+07\n"
