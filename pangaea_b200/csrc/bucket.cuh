@@ -46,7 +46,11 @@ constexpr int kMaxBuckets = 64;
 #ifndef PG_CHUNK
 #define PG_CHUNK 1024
 #endif
-constexpr int kChunk = PG_CHUNK;         // entries per apply ticket (PG_CHUNK / 256 per thread)
+constexpr int kChunk = PG_CHUNK;         // entries per block-wide ticket of the L2 count apply (PG_CHUNK / 256 per thread)
+#ifndef PG_FEAT_CHUNK
+#define PG_FEAT_CHUNK 2048
+#endif
+constexpr int kFeatChunk = PG_FEAT_CHUNK; // entries per warp-wide ticket of the featurize apply (multiple of 128)
 constexpr unsigned long long kOverflowRun = ~0ull;
 constexpr uint32_t kInvalidEntry = 0xFFFFFFFFu; // never a real entry: count entries have low bits 000, deltas stop at 510
 constexpr uint32_t kEntryIndexBits = 0x03FFFFF8u;
@@ -462,6 +466,7 @@ struct ApplySmem {
 };
 
 // saved_fill != nullptr: regions of an earlier scatter launch whose fills were kept (bucket_save_fill_kernel)
+template <int CHUNK = kChunk>
 __device__ __forceinline__ void apply_prologue(ApplySmem& A, const BucketGeom& geo, const BucketState* st, const unsigned long long* saved_fill = nullptr)
 {
     if (threadIdx.x == 0) {
@@ -470,7 +475,7 @@ __device__ __forceinline__ void apply_prologue(ApplySmem& A, const BucketGeom& g
             const unsigned long long f = saved_fill ? saved_fill[b] : min(min(st->cursors[b], st->limits[b]), geo.cap);
             A.fill[b] = f;
             A.chunk_base[b] = acc;
-            acc += (f + kChunk - 1) / kChunk;
+            acc += (f + CHUNK - 1) / CHUNK;
         }
         A.chunk_base[geo.n_buckets] = acc;
     }
@@ -530,58 +535,59 @@ __global__ void __launch_bounds__(256)
 bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __restrict__ meta, BucketGeom geo,
                          BucketState* __restrict__ st, const unsigned long long* __restrict__ saved_fill, const FeatParams P)
 {
+    // Tickets are taken per WARP (kFeatChunk entries each): no block-wide barrier in the loop, so a warp that drew a slow
+    // chunk (more distinct tallies) does not hold seven others back.  The order of the sweep is the order of the tickets.
     __shared__ ApplySmem A;
-    apply_prologue(A, geo, st, SHARED ? saved_fill : nullptr);
+    apply_prologue<kFeatChunk>(A, geo, st, SHARED ? saved_fill : nullptr);
     const unsigned long long n_chunks = A.chunk_base[geo.n_buckets];
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) A.ticket = atomicAdd(&st->ticket, 1ull);
-    __syncthreads();
+    unsigned long long c = 0ull;
+    if (lane == 0) c = atomicAdd(&st->ticket, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
     int b = 0;
-    for (;;) {
-        const unsigned long long c = A.ticket;
+    while (c < n_chunks) {
         unsigned long long next = 0ull;
-        __syncthreads(); // everyone has read A.ticket
-        if (threadIdx.x == 0) next = atomicAdd(&st->ticket, 1ull); // in flight while the chunk is processed
-        if (c >= n_chunks) break;
+        if (lane == 0) next = atomicAdd(&st->ticket, 1ull); // in flight while the chunk is processed
         while (A.chunk_base[b + 1] <= c) ++b;
-        const unsigned long long off = (unsigned long long)b * geo.cap + (c - A.chunk_base[b]) * kChunk; // multiple of 32
-        const uint32_t n = (uint32_t)min((unsigned long long)kChunk, A.fill[b] - (c - A.chunk_base[b]) * kChunk);
-        const uint32_t* src = entries + off;
-        const int32_t* row0_of = meta + (off >> 5);
+        const unsigned long long off = (unsigned long long)b * geo.cap + (c - A.chunk_base[b]) * kFeatChunk; // multiple of 32
+        const uint32_t n = (uint32_t)min((unsigned long long)kFeatChunk, A.fill[b] - (c - A.chunk_base[b]) * kFeatChunk);
         const uint32_t* slice = P.table.counts + ((size_t)b << kSliceBits);
-        uint32_t e[kChunk / 256], cnt[kChunk / 256];
-        int32_t row0[kChunk / 256];
+        for (uint32_t sb = 0; sb < n; sb += 128u) { // 128 entries at a time: 4 per lane in flight
+            const uint32_t* src = entries + off + sb;
+            const int32_t* row0_of = meta + ((off + sb) >> 5);
+            uint32_t e[4], cnt[4];
+            int32_t row0[4];
 #pragma unroll
-        for (int u = 0; u < kChunk / 256; ++u) {
-            const uint32_t i = threadIdx.x + 256u * u;
-            e[u] = i < n ? __ldcs(src + i) : kInvalidEntry;
-            row0[u] = i < n ? __ldg(row0_of + (i >> 5)) : 0; // one base row per warp-wide group of 32 entries
-        }
-#pragma unroll
-        for (int u = 0; u < kChunk / 256; ++u)
-            cnt[u] = (e[u] != kInvalidEntry && !(SHARED && delta_of_entry(e[u]) == kDeltaCountOnly)) ? __ldg(slice + ((e[u] >> 3) & geo.low_mask)) : 0u;
-#pragma unroll
-        for (int u = 0; u < kChunk / 256; ++u) {
-            // the 32 entries of a warp share row0: (delta, bin) identifies the tally inside the warp in 22 bits
-            const uint32_t delta = delta_of_entry(e[u]);
-            uint32_t c32 = cnt[u] & kCountMask;
-            bool live = cnt[u] != 0u && c32 < P.clamp; // absent k-mers are skipped (count_kmer.cpp:87); cnt = 0 for padding
-            int32_t row = row0[u] + (int32_t)delta;
-            if (SHARED) { // row0 is the tile's first cloud: cloud -> row (lanes of a warp hit 1-3 addresses); dropped clouds fall out here
-                live = live && delta != kDeltaCountOnly;
-                row = live ? __ldg(P.row_of_group + row) : -1;
-                live = row >= 0;
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = sb + lane + 32u * u;
+                e[u] = i < n ? __ldcs(src + lane + 32u * u) : kInvalidEntry;
+                row0[u] = i < n ? __ldg(row0_of + u) : 0; // one base row per warp-wide group of 32 entries
             }
-            const uint32_t key = (delta << 13) | (live ? abd_bin(P, c32) : 0u); // vector_size <= 8192
-            const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
-            if (live) {
-                const uint32_t peers = __match_any_sync(live_mask, key);
-                if (lane == __ffs(peers) - 1)
-                    atomicAdd(P.abd + (int64_t)row * P.vs + (key & 0x1FFFu), (uint32_t)__popc(peers));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                cnt[u] = (e[u] != kInvalidEntry && !(SHARED && delta_of_entry(e[u]) == kDeltaCountOnly)) ? __ldg(slice + ((e[u] >> 3) & geo.low_mask)) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // the 32 entries of a warp share row0: (delta, bin) identifies the tally inside the warp in 22 bits
+                const uint32_t delta = delta_of_entry(e[u]);
+                uint32_t c32 = cnt[u] & kCountMask;
+                bool live = cnt[u] != 0u && c32 < P.clamp; // absent k-mers are skipped (count_kmer.cpp:87); cnt = 0 for padding
+                int32_t row = row0[u] + (int32_t)delta;
+                if (SHARED) { // row0 is the tile's first cloud: cloud -> row (lanes of a warp hit 1-3 addresses); dropped clouds fall out here
+                    live = live && delta != kDeltaCountOnly;
+                    row = live ? __ldg(P.row_of_group + row) : -1;
+                    live = row >= 0;
+                }
+                const uint32_t key = (delta << 13) | (live ? abd_bin(P, c32) : 0u); // vector_size <= 8192
+                const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+                if (live) {
+                    const uint32_t peers = __match_any_sync(live_mask, key);
+                    if (lane == __ffs(peers) - 1)
+                        atomicAdd(P.abd + (int64_t)row * P.vs + (key & 0x1FFFu), (uint32_t)__popc(peers));
+                }
             }
         }
-        if (threadIdx.x == 0) A.ticket = next;
-        __syncthreads();
+        c = __shfl_sync(0xffffffffu, next, 0);
     }
 }
 
