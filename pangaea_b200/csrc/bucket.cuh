@@ -299,7 +299,8 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
         if (j < Q.w1) {
             const uint32_t mlo = __ldg(Q.mask + j);
             if (mlo != 0u) {
-                v0 = window_valid_mask(mlo, __ldg(Q.mask + j + 1), k);
+                const uint32_t mhi = __ldg(Q.mask + j + 1);
+                v0 = window_valid_mask(mlo, mhi, k);
                 if (MODE == kScatterFeat && v0) {
                     const uint32_t gw = __ldg(P.wg + j);
                     const uint32_t g = gw & ~kWordMixed;
@@ -328,8 +329,9 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 if (MODE == kScatterShared && v0) {
                     const uint32_t gw = __ldg(P.wg + j);
                     const uint32_t delta = (gw & ~kWordMixed) - (uint32_t)tile_base;
-                    const uint32_t mf = __ldg(P.maskF + j);
-                    const uint32_t vf = mf ? (window_valid_mask(mf, __ldg(P.maskF + j + 1), k) & v0) : 0u;
+                    const uint32_t mf = __ldg(P.maskF + j), mf1 = __ldg(P.maskF + j + 1);
+                    // same mask words as the count mask (no lower case, no NOFEAT read here - the usual case): same windows
+                    const uint32_t vf = (mf == mlo && mf1 == mhi) ? v0 : (mf ? (window_valid_mask(mf, mf1, k) & v0) : 0u);
                     v2 = v0 & ~vf;
                     v0 = vf;
                     d0 = delta_bits(delta);
@@ -404,7 +406,9 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             if (gb != kOverflowRun) {
                 const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
                 uint4* dst = reinterpret_cast<uint4*>(Q.entries + gb);
-                for (uint32_t e = 4u * lane; e < n_pad; e += 128u) {
+                uint32_t e = 4u * lane;
+                for (; e + 4u <= n; e += 128u) __stcs(dst + (e >> 2), *reinterpret_cast<const uint4*>(src + e)); // whole quads
+                if (e < n_pad) { // the quad that holds the end of the run, and the padding after it
                     uint4 v = *reinterpret_cast<const uint4*>(src + e);
                     if (e + 0u >= n) v.x = kInvalidEntry;
                     if (e + 1u >= n) v.y = kInvalidEntry;
