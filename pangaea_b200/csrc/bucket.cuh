@@ -368,7 +368,10 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 for (int q = 0; q < 4; ++q) slot[q] = atomicAdd(cnt + bk[q], 1u);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) // a row that overflows is redone below
+                {
+                    PG_CHECK(bk[q] <= (uint32_t)kMaxBuckets && (bk[q] == (uint32_t)kMaxBuckets || (int)bk[q] < Q.geo.n_buckets));
                     stage[bk[q] * STRIDE + min(slot[q], (uint32_t)(CAP - 1))] = FEAT ? ((yb[q] & kEntryIndexBits) | d) : yb[q];
+                }
             });
         }
         __syncthreads();
@@ -405,6 +408,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             const unsigned long long gb = S.gbase[b];
             if (gb != kOverflowRun) {
                 const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
+                PG_CHECK(n <= (uint32_t)CAP && gb >= (unsigned long long)b * Q.geo.cap && gb + n_pad <= (unsigned long long)(b + 1) * Q.geo.cap && (gb & 3ull) == 0ull);
                 uint4* dst = reinterpret_cast<uint4*>(Q.entries + gb);
                 uint32_t e = 4u * lane;
                 for (; e + 4u <= n; e += 128u) __stcs(dst + (e >> 2), *reinterpret_cast<const uint4*>(src + e)); // whole quads
@@ -579,6 +583,7 @@ bucket_apply_feat_kernel(const uint32_t* __restrict__ entries, const int32_t* __
                 int32_t row = row0[u] + (int32_t)delta;
                 if (SHARED) { // row0 is the tile's first cloud: cloud -> row (lanes of a warp hit 1-3 addresses); dropped clouds fall out here
                     live = live && delta != kDeltaCountOnly;
+                    PG_CHECK(!live || (row >= 0 && row < P.n_groups));
                     row = live ? __ldg(P.row_of_group + row) : -1;
                     live = row >= 0;
                 }

@@ -138,6 +138,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
             const uint16_t* row = stage + s * kSplitStride;
             const uint32_t o = S.off[s];
             if (o != kSubOverflow) {
+                PG_CHECK(m <= (uint32_t)kSplitCap && (o & 7u) == 0u && (unsigned long long)o + ((m + 7u) & ~7u) <= sg.cap);
                 uint4* dst = reinterpret_cast<uint4*>(entries2 + (unsigned long long)(b * kSubFan + s) * sg.cap + o);
                 for (uint32_t i = 8u * (lane & 7); i < m; i += 64u) {
                     uint4 v = *reinterpret_cast<const uint4*>(row + i);
@@ -234,6 +235,7 @@ sub_apply_kernel(const uint16_t* __restrict__ entries2, SubGeom sg, SubState ss,
         const uint32_t first = __ldg(ss.item_base + i), n_chunks = __ldg(ss.item_base + i + 1) - first;
         const uint32_t fill = min(min(ss.cursors[i], ss.limits[i]), sg.cap); // multiple of 8
         const uint32_t start = (item - first) * sg.chunk;
+        PG_CHECK(start < fill && (fill & 7u) == 0u && fill <= sg.cap);
         const uint32_t n8 = min(sg.chunk, fill - start) >> 3;
         const uint4* src = reinterpret_cast<const uint4*>(entries2 + (unsigned long long)i * sg.cap + start); // 16 B aligned: cap, chunk multiples of 8
         for (uint32_t base = 0; base < n8; base += kDepth * kSubApplyThreads) {

@@ -21,6 +21,18 @@
 #define PG_HD inline
 #endif
 
+// -DPG_DEBUG_BOUNDS: device-side range checks on the partition buffers (compute-sanitizer is not available on the
+// measurement pool; `nvcc ... -DPG_DEBUG_BOUNDS -o build/libpg_debug.so`, run the GPU tests with PG_LIB_PATH pointing at it)
+#if defined(PG_DEBUG_BOUNDS) && defined(__CUDA_ARCH__)
+#include <cstdio>
+#define PG_CHECK(cond)                                                                                    \
+    do {                                                                                                  \
+        if (!(cond)) { printf("PG_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); }    \
+    } while (0)
+#else
+#define PG_CHECK(cond) ((void)0)
+#endif
+
 namespace pg {
 
 PG_HD uint64_t low_mask64(int bits) { return bits >= 64 ? ~0ull : ((1ull << bits) - 1ull); }
