@@ -59,8 +59,9 @@ struct pg_ctx {
     int sm_count = 148;
     // table
     uint32_t* counts = nullptr;
-    unsigned long long* keys = nullptr;
+    HashSlot* slots = nullptr; // hash mode
     uint64_t n_slots = 0;
+    bool have_table() const { return counts != nullptr || slots != nullptr; }
     uint32_t* d_overflow = nullptr;
     bool counted = false;
     cudaEvent_t table_event = nullptr; // pending external write to the table (pg_table_wait_event); not owned
@@ -283,7 +284,7 @@ extern "C" const char* pg_last_error(const pg_ctx* ctx) { return ctx ? ctx->err.
 static TableView view(pg_ctx* c)
 {
     TableView t;
-    t.counts = c->counts; t.keys = c->keys; t.capacity_mask = c->n_slots ? c->n_slots - 1 : 0;
+    t.counts = c->counts; t.slots = c->slots; t.capacity_mask = c->n_slots ? c->n_slots - 1 : 0;
     t.overflow = c->d_overflow; t.k = c->p.k;
     return t;
 }
@@ -292,10 +293,9 @@ static int alloc_hash(pg_ctx* ctx, uint64_t slots)
 {
     CK(cudaSetDevice(ctx->p.device));
     ctx->n_slots = slots;
-    CK(cudaMalloc((void**)&ctx->keys, slots * sizeof(unsigned long long)));
-    CK(cudaMalloc((void**)&ctx->counts, slots * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(ctx->keys, 0xFF, slots * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->counts, 0, slots * sizeof(uint32_t), ctx->stream));
+    CK(cudaMalloc((void**)&ctx->slots, slots * sizeof(HashSlot)));
+    hash_clear_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->slots, slots);
+    CK(cudaGetLastError());
     return PG_OK;
 }
 
@@ -397,7 +397,7 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     for (auto e : ctx->pool) cudaEventDestroy(e);
     for (auto& kv : ctx->big.free_blocks) cudaFree(kv.second); // (live blocks belong to batches / feature sets still around)
     cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p); cudaFree(ctx->ws_stash.p);
-    cudaFree(ctx->counts); cudaFree(ctx->keys); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
+    cudaFree(ctx->counts); cudaFree(ctx->slots); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -595,7 +595,7 @@ extern "C" int pg_table_clear(pg_ctx* ctx)
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     if (ctx->counts) CK(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
-    if (ctx->keys) CK(cudaMemsetAsync(ctx->keys, 0xFF, ctx->n_slots * sizeof(unsigned long long), ctx->stream));
+    if (ctx->slots) hash_clear_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->slots, ctx->n_slots);
     CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(uint32_t), ctx->stream));
     ctx->counted = false;
     return PG_OK;
@@ -603,7 +603,7 @@ extern "C" int pg_table_clear(pg_ctx* ctx)
 
 static int ensure_table(pg_ctx* ctx, int64_t hint_windows)
 {
-    if (ctx->counts) return PG_OK;
+    if (ctx->have_table()) return PG_OK;
     // hash mode, capacity not given: 2x the number of windows of the first batch, within [2^20, 2^33]
     uint64_t want = 2 * (uint64_t)std::max<int64_t>(hint_windows, 1), slots = 1ull << 20;
     while (slots < want && slots < (1ull << 33)) slots <<= 1;
@@ -894,7 +894,7 @@ extern "C" int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* out, in
     if (!n) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
-    if (!ctx->counts) { memset(out, 0, (size_t)n * sizeof(uint32_t)); return PG_OK; }
+    if (!ctx->have_table()) { memset(out, 0, (size_t)n * sizeof(uint32_t)); return PG_OK; }
     uint64_t* dk; uint32_t* dc;
     CK(dmalloc(ctx, &dk, (size_t)n)); CK(dmalloc(ctx, &dc, (size_t)n));
     CK(cudaMemcpyAsync(dk, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -910,11 +910,12 @@ extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
 {
     if (!ctx || !n_distinct) return fail(ctx, PG_ERR_INVALID, "pg_table_size: bad argument");
     *n_distinct = 0;
-    if (!ctx->counts) return PG_OK;
+    if (!ctx->have_table()) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
-    table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, (unsigned long long*)ctx->d_scalar);
+    if (ctx->mode == kDense) table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, 1, (unsigned long long*)ctx->d_scalar);
+    else table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(&ctx->slots[0].count, ctx->n_slots, 4, (unsigned long long*)ctx->d_scalar);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -926,7 +927,7 @@ extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts
 {
     if (!ctx || !keys_out || !counts_out || cap < 0 || !n_out) return fail(ctx, PG_ERR_INVALID, "pg_table_export: bad argument");
     *n_out = 0;
-    if (!ctx->counts || !cap) return PG_OK;
+    if (!ctx->have_table() || !cap) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     uint64_t* dk; uint32_t* dc;
@@ -1070,7 +1071,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
 {
     if (!ctx || !b || !out || n_groups < 1 || !group_keep) return fail(ctx, PG_ERR_INVALID, "pg_featurize: bad argument");
     *out = nullptr;
-    if (!ctx->counted || !ctx->counts) return fail(ctx, PG_ERR_STATE, "pg_featurize: the k-mer table is empty - call pg_count / pg_table_set first");
+    if (!ctx->counted || !ctx->have_table()) return fail(ctx, PG_ERR_STATE, "pg_featurize: the k-mer table is empty - call pg_count / pg_table_set first");
     if (n_groups > 0x7FFFFFFFll) return fail(ctx, PG_ERR_INVALID, "more than 2^31 clouds in one batch");
     CK(cudaSetDevice(ctx->p.device));
 

@@ -8,7 +8,9 @@
 //         probe sequence has length 1.  k = 15 (the production default): 2^29
 //         counters = 2 GiB - 1 % of a B200's HBM.
 //   HASH  (k <= 31): lock-free open addressing, linear probing, u64 keys claimed with
-//         atomicCAS, u32 counters bumped with atomicAdd (no-return => RED).
+//         atomicCAS, u32 counters bumped with atomicAdd (no-return => RED).  Key and counter
+//         sit in one 16-byte slot, i.e. in the same 32 B DRAM sector: an insert or a look-up
+//         that finds its key in the first slot touches one sector, not two.
 // Counter updates are fire-and-forget reductions; nothing waits on a round trip.
 #pragma once
 #include <stdint.h>
@@ -25,9 +27,16 @@ constexpr uint32_t kPresentZero = 0x80000000u;
 constexpr uint32_t kCountMask = 0x7FFFFFFFu;
 enum TableMode { kDense = 0, kHash = 1 };
 
+struct HashSlot {
+    unsigned long long key;
+    uint32_t count;
+    uint32_t pad;
+};
+static_assert(sizeof(HashSlot) == 16, "one slot = half a DRAM sector");
+
 struct TableView {
-    uint32_t* counts;              // dense: counters; hash: values
-    unsigned long long* keys;      // hash only
+    uint32_t* counts;              // dense: counters
+    HashSlot* slots;               // hash: key + counter per slot
     uint64_t capacity_mask;        // hash: slots - 1
     uint32_t* overflow;            // hash: set to 1 when an insert finds no slot
     int k;
@@ -42,10 +51,10 @@ __device__ __forceinline__ void table_add_hash(const TableView& t, uint64_t key,
 {
     uint64_t slot = mix64(key) & t.capacity_mask;
     for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
-        unsigned long long cur = *((volatile unsigned long long*)(t.keys + slot));
-        if (cur == kEmptyKey) cur = atomicCAS(t.keys + slot, kEmptyKey, (unsigned long long)key);
+        unsigned long long cur = *((volatile unsigned long long*)&t.slots[slot].key);
+        if (cur == kEmptyKey) cur = atomicCAS(&t.slots[slot].key, kEmptyKey, (unsigned long long)key);
         if (cur == kEmptyKey || cur == key) {
-            atomicAdd(t.counts + slot, n);
+            atomicAdd(&t.slots[slot].count, n);
             return;
         }
         slot = (slot + 1) & t.capacity_mask;
@@ -57,9 +66,9 @@ __device__ __forceinline__ uint32_t table_get_hash(const TableView& t, uint64_t 
 {
     uint64_t slot = mix64(key) & t.capacity_mask;
     for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
-        unsigned long long cur = __ldg(t.keys + slot);
-        if (cur == key) return __ldg(t.counts + slot);
-        if (cur == kEmptyKey) return 0u;
+        const ulonglong2 s2 = __ldg(reinterpret_cast<const ulonglong2*>(t.slots + slot)); // key and counter in one 16 B load
+        if (s2.x == key) return (uint32_t)s2.y;
+        if (s2.x == kEmptyKey) return 0u;
         slot = (slot + 1) & t.capacity_mask;
     }
     return 0u;
@@ -79,8 +88,8 @@ __global__ void table_set_kernel(TableView t, int mode, const uint64_t* __restri
         uint64_t key = canonical_of_fwd(v, t.k);
         uint64_t slot = mix64(key) & t.capacity_mask;
         for (uint64_t probe = 0; probe <= t.capacity_mask; ++probe) {
-            unsigned long long cur = atomicCAS(t.keys + slot, kEmptyKey, (unsigned long long)key);
-            if (cur == kEmptyKey || cur == key) { t.counts[slot] = counts[i] ? counts[i] : kPresentZero; return; }
+            unsigned long long cur = atomicCAS(&t.slots[slot].key, kEmptyKey, (unsigned long long)key);
+            if (cur == kEmptyKey || cur == key) { t.slots[slot].count = counts[i] ? counts[i] : kPresentZero; return; }
             slot = (slot + 1) & t.capacity_mask;
         }
         *t.overflow = 1u;
@@ -95,12 +104,20 @@ __global__ void table_get_kernel(TableView t, int mode, const uint64_t* __restri
     out[i] = (mode == kDense ? t.counts[dense_index_of_fwd(v, t.k)] : table_get_hash(t, canonical_of_fwd(v, t.k))) & kCountMask;
 }
 
-// number of non-zero counters (distinct k-mers)
-__global__ void table_nonzero_kernel(const uint32_t* __restrict__ counts, uint64_t n, unsigned long long* __restrict__ total)
+// empty hash table: every key = kEmptyKey, every counter = 0
+__global__ void hash_clear_kernel(HashSlot* __restrict__ slots, uint64_t n)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const ulonglong2 empty = make_ulonglong2(kEmptyKey, 0ull);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) reinterpret_cast<ulonglong2*>(slots)[i] = empty;
+}
+
+// number of non-zero counters (distinct k-mers); stride_words = 1 for the dense counters, 4 for the counter of a HashSlot
+__global__ void table_nonzero_kernel(const uint32_t* __restrict__ counts, uint64_t n, int stride_words, unsigned long long* __restrict__ total)
 {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long c = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += counts[i] != 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += counts[i * stride_words] != 0;
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
@@ -112,11 +129,11 @@ __global__ void table_export_kernel(TableView t, int mode, uint64_t n_slots, uin
 {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        uint32_t c = t.counts[i];
+        uint32_t c = mode == kDense ? t.counts[i] : t.slots[i].count;
         if (!c) continue;
         unsigned long long at = atomicAdd(cursor, 1ull);
         if (at < cap) {
-            keys_out[at] = mode == kDense ? key_of_dense_index(i, t.k) : (uint64_t)t.keys[i];
+            keys_out[at] = mode == kDense ? key_of_dense_index(i, t.k) : (uint64_t)t.slots[i].key;
             counts_out[at] = c & kCountMask;
         }
     }
