@@ -19,6 +19,13 @@
 
 namespace pg {
 
+// insert `n` occurrences of `key`, the home slot's key already loaded as `cur` (hash mode)
+__device__ __forceinline__ void table_add_hash_probed(const TableView& t, uint64_t key, uint32_t n, uint64_t slot, unsigned long long cur)
+{
+    if (cur == key) { atomicAdd(&t.slots[slot].count, n); return; } // the usual case after the first occurrence: one RED
+    table_add_hash(t, key, n);                                      // empty or taken home slot: claim / probe
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 count_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ maskC, int64_t n_words, TableView t)
@@ -32,6 +39,31 @@ count_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ ma
         if (mlo == 0u) continue; // no window can start on an invalid base
         const uint32_t mhi = maskC[j + 1];
         const uint64_t lo = codes[j], hi = codes[j + 1];
+        if (MODE == kHash) {
+            // eight windows at a time: their home slots are read together (eight sectors in flight per thread instead of
+            // one), then every window whose key is already there costs a single RED
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+                uint64_t key[8], slot[8];
+                unsigned long long cur[8];
+                uint32_t ok = 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u;
+                    const uint32_t mw = __funnelshift_r(mlo, mhi, i);
+                    const uint64_t w = (i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & wmask;
+                    key[u] = canonical_of_window(w, k);
+                    slot[u] = mix64(key[u]) & t.capacity_mask;
+                    if ((mw & km) == km) ok |= 1u << u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cur[u] = (ok >> u) & 1u ? *((volatile unsigned long long*)&t.slots[slot[u]].key) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if ((ok >> u) & 1u) table_add_hash_probed(t, key[u], 1u, slot[u], cur[u]);
+            }
+            continue;
+        }
         uint64_t cur = 0;
         uint32_t run = 0;
 #pragma unroll
@@ -39,21 +71,13 @@ count_kernel(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ ma
             const uint32_t mw = __funnelshift_r(mlo, mhi, i);
             if ((mw & km) != km) continue;
             const uint64_t w = (i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo) & wmask;
-            uint64_t key;
-            if (MODE == kDense) key = dense_index_of_window((uint32_t)w, k);
-            else key = canonical_of_window(w, k);
+            const uint64_t key = dense_index_of_window((uint32_t)w, k);
             if (run && key == cur) { ++run; continue; }
-            if (run) {
-                if (MODE == kDense) table_add_dense(t, (uint32_t)cur, run);
-                else table_add_hash(t, cur, run);
-            }
+            if (run) table_add_dense(t, (uint32_t)cur, run);
             cur = key;
             run = 1;
         }
-        if (run) {
-            if (MODE == kDense) table_add_dense(t, (uint32_t)cur, run);
-            else table_add_hash(t, cur, run);
-        }
+        if (run) table_add_dense(t, (uint32_t)cur, run);
     }
 }
 
