@@ -106,11 +106,10 @@ tnf_kernel(const FeatParams P)
                 }
             }
         }
-        __syncthreads();
-
-        // slot 0 stays in shared memory while the next tile continues the same single cloud
+        // slot 0 stays in shared memory while the next tile continues the same single cloud (no barrier needed then)
         const bool carry = g_hi == g_lo && tile_end < w_end && (__ldg(P.wg + tile_end) & ~kWordMixed) == g_lo;
         if (!carry) {
+            __syncthreads();
             const uint32_t ns = min((uint32_t)n_slots, g_hi - g_lo + 1u);
             for (uint32_t s = 0; s < ns; ++s) {
                 const int32_t row = __ldg(P.row_of_group + g_lo + s);
