@@ -128,6 +128,8 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
             }
             S.n_run[s] = m;
             S.off[s] = o;
+            for (uint32_t i = m; i < ((m + 7u) & ~7u); ++i) stage[s * kSplitStride + i] = kSubInvalid; // pad the run to whole 16 B quads here,
+                                                                                                      // so the copy below is a plain loop
             if (over) atomicOr(&S.ovf[s >> 5], 1u << (s & 31));
         }
         __syncthreads();
@@ -140,20 +142,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
             if (o != kSubOverflow) {
                 PG_CHECK(m <= (uint32_t)kSplitCap && (o & 7u) == 0u && (unsigned long long)o + ((m + 7u) & ~7u) <= sg.cap);
                 uint4* dst = reinterpret_cast<uint4*>(entries2 + (unsigned long long)(b * kSubFan + s) * sg.cap + o);
-                for (uint32_t i = 8u * (lane & 7); i < m; i += 64u) {
-                    uint4 v = *reinterpret_cast<const uint4*>(row + i);
-                    const uint32_t left = m - i; // >= 1 valid entries from i on
-                    if (left < 8u) {
-                        uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (2u * c >= left) w[c] = (uint32_t)kSubInvalid | ((uint32_t)kSubInvalid << 16);
-                            else if (2u * c + 1u >= left) w[c] = (w[c] & 0xFFFFu) | ((uint32_t)kSubInvalid << 16);
-                        }
-                        v = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    __stcs(dst + (i >> 3), v);
-                }
+                for (uint32_t i = 8u * (lane & 7); i < m; i += 64u) __stcs(dst + (i >> 3), *reinterpret_cast<const uint4*>(row + i));
             } else { // sub-region full: apply the run here
                 uint32_t* sub_table = table + ((size_t)b << kSliceBits) + ((size_t)s << kSubBits);
                 for (uint32_t i = lane & 7; i < m; i += 8) atomicAdd(sub_table + row[i], 1u);
