@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l; free -g | head -2
-for n in 8; do
+for n in 8 4; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/scale_$n.log 2> gpurun_out/scale_$n.err
   python - <<PY
 import json
