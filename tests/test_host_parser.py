@@ -156,3 +156,39 @@ def test_reference_csv_writer_matches_the_reference_tools(tmp_path, golden):
     big = np.array([[1114930, 3, 999999, 1000000, 12345678]])
     write_reference_csv(str(tmp_path / "big.gz"), ["AC"], big)
     assert gzip.open(tmp_path / "big.gz", "rt").read() == "AC,1.11493e+06,3,999999,1e+06,1.23457e+07\n"
+
+
+def test_parallel_reader_property_random_text(tmp_path, monkeypatch):
+    """Property test (hypothesis): on arbitrary hostile text - blank lines, '\\r', headers with or without BX / '#', records cut
+    anywhere, no final newline - the parallel reader returns exactly what the sequential one returns."""
+    from hypothesis import given, settings, strategies as st
+
+    header = st.one_of(
+        st.builds(lambda n, bc: b"@r%d BX:Z:%s-1" % (n, bc), st.integers(0, 99), st.sampled_from([b"AAAA", b"AAAC", b"CC", b"", b"GG-TT"])),
+        st.builds(lambda n, bc, m: b"@r%d#%s/%d" % (n, bc, m), st.integers(0, 99), st.sampled_from([b"1_1_1", b"0_0_0", b"2_2_2", b""]), st.integers(1, 2)),
+        st.sampled_from([b"@plain", b"", b"@x\tBX:Z:AAAA", b"@y BX:Z:", b"# /", b"@z\r"]))
+    seq = st.one_of(st.text(alphabet="ACGTNacgt", min_size=0, max_size=40).map(str.encode), st.sampled_from([b"", b"ACGT\r", b"@ACGT", b"+"]))
+    line = st.one_of(header, seq, st.sampled_from([b"+", b"IIII", b"", b"????"]))
+    record = st.tuples(header, seq, st.just(b"+"), seq).map(lambda t: list(t))
+    text = st.one_of(st.lists(record, max_size=24).map(lambda rs: [l for r in rs for l in r]), st.lists(line, max_size=60))
+
+    counter = [0]
+
+    @settings(max_examples=400, deadline=None)
+    @given(lines=text, final_newline=st.booleans(), threads=st.sampled_from(["2", "3", "5"]))
+    def check(lines, final_newline, threads):
+        counter[0] += 1
+        path = str(tmp_path / f"h{counter[0] % 4}.fq")
+        data = b"\n".join(lines) + (b"\n" if final_newline and lines else b"")
+        open(path, "wb").write(data)
+        monkeypatch.setenv("PG_FASTQ_THREADS", "1")
+        want = _parse_all(path, want_qual=True)
+        monkeypatch.setenv("PG_FASTQ_THREADS", threads)
+        monkeypatch.setenv("PG_FASTQ_PARALLEL_MIN", "0")
+        got = _parse_all(path, want_qual=True)
+        monkeypatch.delenv("PG_FASTQ_PARALLEL_MIN")
+        for a, b in zip(want[:4], got[:4]):
+            assert np.array_equal(a, b), data
+        assert want[4] == got[4] and want[5] == got[5], data
+
+    check()
