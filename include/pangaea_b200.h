@@ -53,7 +53,7 @@ typedef enum pg_status {
 } pg_status;
 
 enum { PG_READ_CHANGE = 1, PG_READ_NOFEAT = 2 };
-enum { PG_TABLE_AUTO = 0, PG_TABLE_DENSE = 1, PG_TABLE_HASH = 2 };
+enum { PG_TABLE_AUTO = 0, PG_TABLE_DENSE = 1, PG_TABLE_HASH = 2, PG_TABLE_NONE = 3 /* no table: a ctx that only normalises (Data.__init__) */ };
 
 /* Replaces the CLI flags of count_kmer (count_kmer.cpp:112-123) / count_tnf
  * (count_tnf.cpp:117-125) as passed by feature.py:107-109,131-133, and the
@@ -66,7 +66,9 @@ typedef struct pg_params {
     int32_t vector_size;     /* -v, 400: abundance bins */
     int64_t min_length;      /* -l, 2000: clouds with sum(len+1) <= this are dropped */
     int32_t min_qual_char;   /* jellyfish --min-qual-char (0 = off; '?' in the -1/-2 branch) */
-    int32_t table_mode;      /* PG_TABLE_*: dense direct-addressed (k <= 16) or open-addressing hash */
+    int32_t table_mode;      /* PG_TABLE_*: dense direct-addressed (k <= 16) or open-addressing hash.  Dense counters saturate at
+                              * 2^31 - 1 (jellyfish would report the true count; count_kmer.cpp:90-92 drops either), which is why
+                              * window_size * vector_size must be <= 2^31 - 1 */
     uint64_t table_capacity; /* hash slots (power of two; 0 = sized from the first batch) */
 } pg_params;
 
@@ -127,6 +129,10 @@ int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entries);
  * or writes the table first waits for `cuda_event` (a cudaEvent_t recorded after that work).  The parts of
  * pg_featurize that do not need the table (cloud grouping, TNF) run ahead of it - they overlap the collective. */
 int pg_table_wait_event(pg_ctx* ctx, void* cuda_event);
+/* dense mode only: counter = min(counter, max_count).  A data-parallel caller clamps every rank's table to
+ * (2^31 - 1) / n_ranks before the int32 sum so that the sum cannot wrap; exact as long as
+ * window_size * vector_size <= max_count (a clamped count is dropped from the histogram like the true one). */
+int pg_table_clamp(pg_ctx* ctx, uint32_t max_count);
 
 /* ---- step 1b: per-cloud abundance histogram + TNF --------------------------- */
 /* replaces bin/count_kmer (countKmer, count_kmer.cpp:55-108) and bin/count_tnf
@@ -143,7 +149,10 @@ int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t* groups_ou
 int pg_features_copy_raw(pg_ctx* ctx, const pg_features* f, int32_t* abd_out, int32_t* tnf_out);
 
 /* ---- step 2 prologue: Data.__init__ (src/data.py:16-21) --------------------- */
-/* L1-normalise both matrices (fp64 divide, fp32 store) and weights = max(abd row)^2 (fp64) */
+/* L1-normalise both matrices (fp64 divide, fp32 store) and weights = max(abd row)^2 (fp64).  The reference normalises
+ * what pandas read back from the tools' CSV text, and `ostream << double` keeps 6 significant digits (count_kmer.cpp:211,
+ * count_tnf.cpp:204): tallies >= 10^6 are rounded the same way (ties to even) before the division.  The raw tallies
+ * (pg_features_copy_raw, DLPack 0/1) stay exact. */
 int pg_normalize(pg_ctx* ctx, pg_features* f);
 int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, float* abd_out, float* tnf_out, double* weights_out);
 

@@ -236,6 +236,19 @@ def data_init(abd: np.ndarray, tnf_: np.ndarray):
     return nabd.astype(np.float32), normalize_l1(tnf_).astype(np.float32), weights
 
 
+def text_round(m: np.ndarray) -> np.ndarray:
+    """What reaches pandas after the tools' CSV round trip: `ostream << double` prints 6 significant digits
+    (count_kmer.cpp:211, count_tnf.cpp:204), so a tally >= 10^6 comes back as float("%.6g" % tally) - KAT-5.
+    Python's % formatting and glibc's printf round the exact decimal value the same way (ties to even)."""
+    m = np.asarray(m)
+    big = m >= 1_000_000
+    if not big.any():
+        return m
+    out = m.astype(np.float64)
+    out[big] = [float("%.6g" % int(v)) for v in m[big]]
+    return out
+
+
 # ----------------------------------------------------------------------------
 # the compiled reference tools
 # ----------------------------------------------------------------------------

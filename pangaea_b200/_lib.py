@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(HERE, "libpangaea_b200.so")  # PG_LIB_PATH: A/B builds (tools/)
 
 PG_READ_CHANGE, PG_READ_NOFEAT = 1, 2
-PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH = 0, 1, 2
+PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH, PG_TABLE_NONE = 0, 1, 2, 3
 T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL, T_COUNT_SCATTER, T_FEAT_SCATTER, T_TNF, T_COUNT_SPLIT = range(10)
 ABD_RAW, TNF_RAW, ABD, TNF, WEIGHTS = range(5)
 
@@ -64,6 +64,7 @@ SIGNATURES = {
     "pg_table_export": (_int, [_vp, _vp, _vp, _i64, _P(_i64)]),
     "pg_table_dense_view": (_int, [_vp, _P(_vp), _P(_i64)]),
     "pg_table_wait_event": (_int, [_vp, _vp]),
+    "pg_table_clamp": (_int, [_vp, C.c_uint32]),
     "pg_featurize": (_int, [_vp, _vp, _vp, _i64, _P(_vp)]),
     "pg_features_free": (None, [_vp, _vp]),
     "pg_features_rows": (_i64, [_vp]),
@@ -316,6 +317,10 @@ class Context:
         self._ck(lib().pg_table_dense_view(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def table_clamp(self, max_count: int):
+        """counter = min(counter, max_count) over the dense table (before an int32 sum across ranks)."""
+        self._ck(lib().pg_table_clamp(self.h, int(max_count)))
+
     def table_wait_event(self, cuda_event: int):
         """Later table readers of this ctx wait for the CUDA event (raw cudaEvent_t, e.g. torch.cuda.Event.cuda_event)."""
         self._ck(lib().pg_table_wait_event(self.h, C.c_void_p(int(cuda_event))))
@@ -328,6 +333,11 @@ class Context:
         import torch.distributed as dist
 
         dev = f"cuda:{self.params.device}"
+        world = dist.get_world_size(group)
+        if world > 1:  # counters saturate at 2^31 - 1: keep the int32 sum of `world` tables below bit 31 (pg_table_clamp)
+            if self.params.window_size * self.params.vector_size > (2 ** 31 - 1) // world:
+                raise PgError(-1, f"window_size * vector_size must be <= (2^31 - 1) / {world} ranks")
+            self.table_clamp((2 ** 31 - 1) // world)
         counted = torch.cuda.Event()
         with torch.cuda.stream(torch.cuda.ExternalStream(self.stream, device=dev)):
             counted.record()

@@ -1,6 +1,7 @@
 // api.cu - C-ABI (include/pangaea_b200.h) over the sm_100a kernels.
 // Host orchestration only: allocation, launches, read-backs.  No CPU compute path.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -61,8 +62,12 @@ struct pg_ctx {
     uint32_t* counts = nullptr;
     HashSlot* slots = nullptr; // hash mode
     uint64_t n_slots = 0;
+    bool no_table = false;     // PG_TABLE_NONE: a ctx that only normalises (Data.__init__) - nothing that needs the table works
     bool have_table() const { return counts != nullptr || slots != nullptr; }
     uint32_t* d_overflow = nullptr;
+    uint32_t* d_sat = nullptr;      // raised by a direct add that takes a dense counter to bit 31 (table.cuh: saturation)
+    bool zero_markers = false;      // pg_table_set stored a "present with count 0" marker: counting on top of it is refused
+    cudaMemPool_t mempool = nullptr; // private pool of the small stream-ordered allocations (the default pool is left alone)
     bool counted = false;
     cudaEvent_t table_event = nullptr; // pending external write to the table (pg_table_wait_event); not owned
     // TNF look-up table
@@ -115,7 +120,7 @@ struct pg_batch {
 };
 
 struct pg_features {
-    int refs = 1;
+    std::atomic<int> refs{ 1 };     // the DLPack deleter may run on any thread
     int device = 0;
     int64_t rows = 0;
     int32_t vs = 0, td = 0;
@@ -225,7 +230,7 @@ static cudaError_t dmalloc(pg_ctx* ctx, T** p, size_t n)
 {
     const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
     if (bytes >= kBigBlock) return big_alloc(ctx, (void**)p, bytes);
-    return cudaMallocAsync((void**)p, bytes, ctx->stream);
+    return cudaMallocFromPoolAsync((void**)p, bytes, ctx->mempool, ctx->stream);
 }
 static void dfree(pg_ctx* ctx, void* p)
 {
@@ -285,7 +290,7 @@ static TableView view(pg_ctx* c)
 {
     TableView t;
     t.counts = c->counts; t.slots = c->slots; t.capacity_mask = c->n_slots ? c->n_slots - 1 : 0;
-    t.overflow = c->d_overflow; t.k = c->p.k;
+    t.overflow = c->d_overflow; t.sat = c->d_sat; t.k = c->p.k;
     return t;
 }
 
@@ -307,10 +312,14 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     if (p->k < 1 || p->k > 31) return fail(nullptr, PG_ERR_INVALID, "k must be in 1..31");
     if (p->tnf_k < 1 || p->tnf_k > 6) return fail(nullptr, PG_ERR_INVALID, "tnf_k must be in 1..6");
     if (p->window_size < 1) return fail(nullptr, PG_ERR_INVALID, "window_size must be >= 1");
-    if (p->vector_size < 1 || p->vector_size > 8192) return fail(nullptr, PG_ERR_INVALID, "vector_size must be in 1..8192");
     int mode = p->table_mode == PG_TABLE_AUTO ? (p->k <= 16 ? PG_TABLE_DENSE : PG_TABLE_HASH) : p->table_mode;
+    if (mode != PG_TABLE_NONE && (p->vector_size < 1 || p->vector_size > 8192)) return fail(nullptr, PG_ERR_INVALID, "vector_size must be in 1..8192");
+    if (p->vector_size < 1) return fail(nullptr, PG_ERR_INVALID, "vector_size must be >= 1");
+    // counters saturate at 2^31 - 1: exact as long as every count that lands in a bin is below that (table.cuh)
+    if ((uint64_t)p->window_size * (uint64_t)p->vector_size > 0x7FFFFFFFull && mode != PG_TABLE_NONE)
+        return fail(nullptr, PG_ERR_INVALID, "window_size * vector_size must be <= 2^31 - 1");
     if (mode == PG_TABLE_DENSE && p->k > 16) return fail(nullptr, PG_ERR_INVALID, "dense table needs k <= 16");
-    if (mode != PG_TABLE_DENSE && mode != PG_TABLE_HASH) return fail(nullptr, PG_ERR_INVALID, "bad table_mode");
+    if (mode != PG_TABLE_DENSE && mode != PG_TABLE_HASH && mode != PG_TABLE_NONE) return fail(nullptr, PG_ERR_INVALID, "bad table_mode");
     if (p->table_capacity & (p->table_capacity - 1)) return fail(nullptr, PG_ERR_INVALID, "table_capacity must be a power of two");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
@@ -321,6 +330,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "out of host memory");
     ctx->p = *p;
     ctx->mode = mode == PG_TABLE_DENSE ? kDense : kHash;
+    ctx->no_table = mode == PG_TABLE_NONE;
     std::vector<uint16_t> lut;
     ctx->td = build_tnf_lut(p->tnf_k, &lut);
 #define CKC(call)                                                                                        \
@@ -336,9 +346,15 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p->device));
-    {   // keep freed blocks in the pool: steady-state steps allocate without touching the driver
-        cudaMemPool_t pool;
-        CKC(cudaDeviceGetDefaultMemPool(&pool, p->device));
+    {   // a pool of its own (other users of cudaMallocAsync in the process keep the default pool's settings); freed blocks
+        // stay in it: steady-state steps allocate without touching the driver
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = p->device;
+        CKC(cudaMemPoolCreate(&ctx->mempool, &props));
+        cudaMemPool_t pool = ctx->mempool;
         uint64_t keep = ~0ull;
         CKC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         // reuse by stream order only: with the opportunistic policies the block a request gets depends on how far the host
@@ -351,6 +367,8 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CKC(cudaMalloc((void**)&ctx->d_overflow, sizeof(uint32_t)));
     CKC(cudaMemset(ctx->d_overflow, 0, sizeof(uint32_t)));
+    CKC(cudaMalloc((void**)&ctx->d_sat, sizeof(uint32_t)));
+    CKC(cudaMemset(ctx->d_sat, 0, sizeof(uint32_t)));
     CKC(cudaMalloc((void**)&ctx->d_scalar, 8 * sizeof(int64_t)));
     CKC(cudaMalloc((void**)&ctx->d_bucket, sizeof(BucketState)));
     { const char* e = getenv("PG_REGION_SLACK"); if (e && atof(e) > 0) ctx->region_slack = atof(e); }
@@ -361,7 +379,9 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     { const char* e = getenv("PG_TNF_OVERLAP"); if (e) ctx->tnf_overlap = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("PG_FEAT_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
-    if (ctx->mode == kDense) {
+    if (ctx->no_table) {
+        // nothing to allocate
+    } else if (ctx->mode == kDense) {
         ctx->n_slots = dense_entries(p->k);
         CKC(cudaMalloc((void**)&ctx->counts, ctx->n_slots * sizeof(uint32_t)));
         CKC(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
@@ -397,10 +417,11 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     for (auto e : ctx->pool) cudaEventDestroy(e);
     for (auto& kv : ctx->big.free_blocks) cudaFree(kv.second); // (live blocks belong to batches / feature sets still around)
     cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p); cudaFree(ctx->ws_stash.p);
-    cudaFree(ctx->counts); cudaFree(ctx->slots); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
+    cudaFree(ctx->counts); cudaFree(ctx->slots); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_sat); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     delete ctx;
 }
 
@@ -597,12 +618,15 @@ extern "C" int pg_table_clear(pg_ctx* ctx)
     if (ctx->counts) CK(cudaMemsetAsync(ctx->counts, 0, ctx->n_slots * sizeof(uint32_t), ctx->stream));
     if (ctx->slots) hash_clear_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->slots, ctx->n_slots);
     CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_sat, 0, sizeof(uint32_t), ctx->stream));
     ctx->counted = false;
+    ctx->zero_markers = false;
     return PG_OK;
 }
 
 static int ensure_table(pg_ctx* ctx, int64_t hint_windows)
 {
+    if (ctx->no_table) return fail(ctx, PG_ERR_STATE, "this ctx was created with PG_TABLE_NONE: it only normalises");
     if (ctx->have_table()) return PG_OK;
     // hash mode, capacity not given: 2x the number of windows of the first batch, within [2^20, 2^33]
     uint64_t want = 2 * (uint64_t)std::max<int64_t>(hint_windows, 1), slots = 1ull << 20;
@@ -684,9 +708,9 @@ static size_t available_bytes(pg_ctx* ctx)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
-    cudaMemPool_t pool;
+    cudaMemPool_t pool = ctx->mempool;
     uint64_t reserved = 0, used = 0;
-    if (cudaDeviceGetDefaultMemPool(&pool, ctx->p.device) == cudaSuccess &&
+    if (pool &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
         free_b += (size_t)(reserved - used);
@@ -778,12 +802,21 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
     return PG_OK;
 }
 
+// end of a count segment (< 2^31 windows): counters that reached bit 31 are clamped to kCountMax (table.cuh: saturation).
+// gated: the kernel returns at once unless a checked add raised the flag during the segment.
+static cudaError_t saturate_if_flagged(pg_ctx* ctx, bool gated)
+{
+    if (ctx->mode != kDense || !ctx->counts) return cudaSuccess;
+    table_saturate_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, kCountMax, gated ? ctx->d_sat : nullptr);
+    return cudaMemsetAsync(ctx->d_sat, 0, sizeof(uint32_t), ctx->stream);
+}
+
 // count the windows that start in words [w0, w1) (w1 - w0 <= plan.seg_words); words w1, w1 + 1 must be packed too
 static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int64_t w1)
 {
     ScatterParams Q = {};
     Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = P.geo; Q.st = ctx->d_bucket;
-    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts; Q.lost = nullptr;
+    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat;
     Q.w0 = w0; Q.w1 = w1;
     FeatParams F = {};
     int rc = PG_OK;
@@ -807,14 +840,16 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
         {
             Timed t(ctx, T_COUNT_SPLIT, 2);
             sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(P.ss, P.sg);
-            bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts);
+            bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts, ctx->d_sat);
         }
         Timed t(ctx, T_COUNT, 2);
         sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(P.ss, P.sg);
-        sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(P.entries2, P.sg, P.ss, ctx->counts);
+        sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(P.entries2, P.sg, P.ss, ctx->counts, ctx->d_sat);
+        CK(saturate_if_flagged(ctx, true));
     } else {
         Timed t(ctx, T_COUNT, 1);
         bucket_apply_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, ctx->counts);
+        CK(saturate_if_flagged(ctx, false)); // plain REDs here (A/B path): clamp unconditionally
     }
     CK(cudaGetLastError());
     return PG_OK;
@@ -835,16 +870,23 @@ extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
+    if (ctx->zero_markers) return fail(ctx, PG_ERR_STATE, "pg_count: the table holds zero-count markers from pg_table_set - call pg_table_clear first");
     int rc = ensure_table(ctx, b->n_bytes);
     if (rc) return rc;
     if (b->n_words && use_buckets(ctx)) {
         rc = count_bucketed(ctx, b);
         if (rc) return rc;
     } else if (b->n_words) {
-        Timed t(ctx, T_COUNT, 1);
-        const int grid = grid_for(b->n_words, 256, ctx->sm_count * 8);
-        if (ctx->mode == kDense) count_kernel<kDense><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, b->n_words, view(ctx));
-        else count_kernel<kHash><<<grid, 256, 0, ctx->stream>>>(b->codes, b->maskC, b->n_words, view(ctx));
+        // launches of < 2^31 windows, each followed by the (gated) clamp: a dense counter cannot wrap (table.cuh: saturation)
+        const int64_t step = 1ll << 26;
+        for (int64_t w0 = 0; w0 < b->n_words; w0 += step) {
+            const int64_t n = std::min(step, b->n_words - w0);
+            Timed t(ctx, T_COUNT, 2);
+            const int grid = grid_for(n, 256, ctx->sm_count * 8);
+            if (ctx->mode == kDense) count_kernel<kDense><<<grid, 256, 0, ctx->stream>>>(b->codes + w0, b->maskC + w0, n, view(ctx));
+            else count_kernel<kHash><<<grid, 256, 0, ctx->stream>>>(b->codes + w0, b->maskC + w0, n, view(ctx));
+            CK(saturate_if_flagged(ctx, true));
+        }
     }
     CK(cudaGetLastError());
     ctx->counted = true;
@@ -860,6 +902,7 @@ extern "C" int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* c
     if (rc) return rc;
     ctx->counted = true;
     if (!n) return PG_OK;
+    for (int64_t i = 0; i < n; ++i) if (counts[i] == 0) { ctx->zero_markers = true; break; }
     uint64_t* dk; uint32_t* dc;
     CK(dmalloc(ctx, &dk, (size_t)n)); CK(dmalloc(ctx, &dc, (size_t)n));
     // one key at a time keeps "last assignment wins" (count_kmer.cpp:166) for duplicate keys:
@@ -914,8 +957,8 @@ extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
     CK(cudaMemsetAsync(ctx->d_scalar, 0, sizeof(int64_t), ctx->stream));
-    if (ctx->mode == kDense) table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, 1, (unsigned long long*)ctx->d_scalar);
-    else table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(&ctx->slots[0].count, ctx->n_slots, 4, (unsigned long long*)ctx->d_scalar);
+    if (ctx->mode == kDense) table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, nullptr, ctx->n_slots, (unsigned long long*)ctx->d_scalar);
+    else table_nonzero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(nullptr, ctx->slots, ctx->n_slots, (unsigned long long*)ctx->d_scalar);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -978,6 +1021,19 @@ extern "C" int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entri
     *dev_ptr = ctx->counts;
     *n_entries = (int64_t)ctx->n_slots;
     ctx->counted = true; // a caller that sums tables across ranks owns the contents
+    return PG_OK;
+}
+
+extern "C" int pg_table_clamp(pg_ctx* ctx, uint32_t max_count)
+{
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    if (ctx->mode != kDense || !ctx->counts) return fail(ctx, PG_ERR_STATE, "pg_table_clamp: table is not dense");
+    if (ctx->zero_markers) return fail(ctx, PG_ERR_STATE, "pg_table_clamp: the table holds zero-count markers from pg_table_set");
+    if (max_count > kCountMax) max_count = kCountMax;
+    CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
+    table_saturate_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, max_count, nullptr);
+    CK(cudaGetLastError());
     return PG_OK;
 }
 
@@ -1222,7 +1278,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 int32_t* const feat_meta = (int32_t*)((uint8_t*)ctx->ws_feat.p + E * 4);
                 ScatterParams Q = {};
                 Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
-                Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts; Q.lost = nullptr;
+                Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat;
                 for (int64_t w0 = covered; w0 < b->n_words; w0 += seg_words) {
                     Q.w0 = w0; Q.w1 = std::min(b->n_words, w0 + seg_words);
                     {
@@ -1266,7 +1322,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
 // the next step's allocations reuse them); the DLPack deleter has no ctx and frees synchronously.
 static void features_release(pg_features* f, pg_ctx* ctx = nullptr)
 {
-    if (--f->refs > 0) return;
+    if (f->refs.fetch_sub(1) > 1) return;
     cudaSetDevice(f->device);
     void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
     for (void* p : bufs) {
@@ -1321,8 +1377,8 @@ extern "C" int pg_normalize(pg_ctx* ctx, pg_features* f)
     if (f->rows) {
         Timed t(ctx, T_NORM, 2);
         const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
-        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights);
-        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr);
+        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
+        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
     }
     CK(cudaGetLastError());
     f->normalized = true;

@@ -237,6 +237,7 @@ struct ScatterParams {
     uint32_t* table;           // count / shared: the dense counters (overflow paths)
     uint32_t* lost;            // shared: set to 1 when an overflow path applied counts directly - the entries of those
                                // windows are missing from the buffer, so the featurize pass must not reuse it
+    uint32_t* sat;             // count / shared: raised when a direct add takes a counter to bit 31 (table.cuh: saturation)
 };
 
 // MODE of the scatter kernel
@@ -434,7 +435,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                     abd_reduce_warp(P, live, key);
                 }
             } else { // region full: apply the run here
-                for (uint32_t e = lane; e < n; e += 32) atomicAdd(Q.table + (((uint32_t)b << kSliceBits) | ((src[e] >> 3) & Q.geo.low_mask)), 1u);
+                for (uint32_t e = lane; e < n; e += 32) table_add_checked(Q.table + (((uint32_t)b << kSliceBits) | ((src[e] >> 3) & Q.geo.low_mask)), 1u, Q.sat);
                 if (MODE == kScatterShared && lane == 0) *Q.lost = 1u;
             }
         }
@@ -447,7 +448,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 const uint32_t y = window_y(lo, hi, i, k);
                 if (!((ovf >> (y >> 26)) & 1ull)) continue;
                 if (MODE == kScatterFeat) abd_direct(P, y, ((v0 >> i) & 1u) ? row0 : row1);
-                else atomicAdd(Q.table + (y >> 3), 1u);
+                else table_add_checked(Q.table + (y >> 3), 1u, Q.sat);
             }
             if (MODE == kScatterShared) *Q.lost = 1u;
         }

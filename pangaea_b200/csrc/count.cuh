@@ -22,7 +22,7 @@ namespace pg {
 // insert `n` occurrences of `key`, the home slot's key already loaded as `cur` (hash mode)
 __device__ __forceinline__ void table_add_hash_probed(const TableView& t, uint64_t key, uint32_t n, uint64_t slot, unsigned long long cur)
 {
-    if (cur == key) { atomicAdd(&t.slots[slot].count, n); return; } // the usual case after the first occurrence: one RED
+    if (cur == key) { atomicAdd(&t.slots[slot].count, (unsigned long long)n); return; } // the usual case after the first occurrence: one RED
     table_add_hash(t, key, n);                                      // empty or taken home slot: claim / probe
 }
 

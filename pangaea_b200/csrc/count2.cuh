@@ -66,7 +66,7 @@ struct SplitSmem {
 
 __global__ void __launch_bounds__(kSplitThreads, 2)
 bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const BucketState* __restrict__ st, SubGeom sg, SubState ss,
-                    uint16_t* __restrict__ entries2, uint32_t* __restrict__ table)
+                    uint16_t* __restrict__ entries2, uint32_t* __restrict__ table, uint32_t* __restrict__ sat)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SplitSmem& S = *reinterpret_cast<SplitSmem*>(smem_raw);
@@ -145,7 +145,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
                 for (uint32_t i = 8u * (lane & 7); i < m; i += 64u) __stcs(dst + (i >> 3), *reinterpret_cast<const uint4*>(row + i));
             } else { // sub-region full: apply the run here
                 uint32_t* sub_table = table + ((size_t)b << kSliceBits) + ((size_t)s << kSubBits);
-                for (uint32_t i = lane & 7; i < m; i += 8) atomicAdd(sub_table + row[i], 1u);
+                for (uint32_t i = lane & 7; i < m; i += 8) table_add_checked(sub_table + row[i], 1u, sat);
             }
         }
         // staging rows that overflowed: those sub-slices' entries of this tile go straight to the table
@@ -154,7 +154,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
                 const uint32_t v = __ldg(entries + (unsigned long long)b * geo.cap + off + i);
                 if (v == kInvalidEntry) continue;
                 const uint32_t sub = (v >> (3 + kSubBits)) & (kSubFan - 1);
-                if ((S.ovf[sub >> 5] >> (sub & 31)) & 1u) atomicAdd(table + ((size_t)b << kSliceBits) + ((v >> 3) & geo.low_mask), 1u);
+                if ((S.ovf[sub >> 5] >> (sub & 31)) & 1u) table_add_checked(table + ((size_t)b << kSliceBits) + ((v >> 3) & geo.low_mask), 1u, sat);
             }
         }
         __syncthreads();
@@ -206,7 +206,7 @@ sub_items_kernel(SubState ss, SubGeom sg)
 }
 
 __global__ void __launch_bounds__(kSubApplyThreads, 1)
-sub_apply_kernel(const uint16_t* __restrict__ entries2, SubGeom sg, SubState ss, uint32_t* __restrict__ table)
+sub_apply_kernel(const uint16_t* __restrict__ entries2, SubGeom sg, SubState ss, uint32_t* __restrict__ table, uint32_t* __restrict__ sat)
 {
     extern __shared__ __align__(16) uint32_t tab[]; // kSubWords counters + 1 dummy (padding entries)
     for (int w = threadIdx.x * 4; w < kSubWords; w += kSubApplyThreads * 4) *reinterpret_cast<uint4*>(tab + w) = make_uint4(0, 0, 0, 0);
@@ -255,7 +255,10 @@ sub_apply_kernel(const uint16_t* __restrict__ entries2, SubGeom sg, SubState ss,
 #pragma unroll
             for (int u = 0; u < kMergePer; ++u) {
                 if (t[u].x | t[u].y | t[u].z | t[u].w) {
-                    g[u].x += t[u].x; g[u].y += t[u].y; g[u].z += t[u].z; g[u].w += t[u].w;
+                    // both terms are < 2^31 (a segment holds < 2^31 windows, the table is <= kCountMax at segment
+                    // boundaries), so the sum cannot wrap: clamp it (table.cuh: saturation)
+                    g[u].x = min(g[u].x + t[u].x, kCountMax); g[u].y = min(g[u].y + t[u].y, kCountMax);
+                    g[u].z = min(g[u].z + t[u].z, kCountMax); g[u].w = min(g[u].w + t[u].w, kCountMax);
                     dst[u * kSubApplyThreads + threadIdx.x] = g[u];
                     reinterpret_cast<uint4*>(tab)[u * kSubApplyThreads + threadIdx.x] = make_uint4(0, 0, 0, 0);
                 }
@@ -264,10 +267,10 @@ sub_apply_kernel(const uint16_t* __restrict__ entries2, SubGeom sg, SubState ss,
 #pragma unroll
             for (int u = 0; u < kMergePer; ++u) {
                 uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + u * kSubApplyThreads + threadIdx.x);
-                if (t[u].x) atomicAdd(d4, t[u].x);
-                if (t[u].y) atomicAdd(d4 + 1, t[u].y);
-                if (t[u].z) atomicAdd(d4 + 2, t[u].z);
-                if (t[u].w) atomicAdd(d4 + 3, t[u].w);
+                if (t[u].x) table_add_checked(d4, t[u].x, sat);
+                if (t[u].y) table_add_checked(d4 + 1, t[u].y, sat);
+                if (t[u].z) table_add_checked(d4 + 2, t[u].z, sat);
+                if (t[u].w) table_add_checked(d4 + 3, t[u].w, sat);
                 if (t[u].x | t[u].y | t[u].z | t[u].w) reinterpret_cast<uint4*>(tab)[u * kSubApplyThreads + threadIdx.x] = make_uint4(0, 0, 0, 0);
             }
         }

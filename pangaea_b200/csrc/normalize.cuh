@@ -8,23 +8,39 @@
 // results are bit-identical, not merely within the 1e-6 the north star allows.
 // max(x_j / s) = max(x_j) / s because correctly rounded division is monotone.
 // One warp per row; reads 4 B and writes 4 B per element (HBM-bound, streaming).
+//
+// Text round trip.  The reference never normalises the tallies themselves but what pandas read back from the
+// tools' CSV, and `ostream << double` prints 6 significant digits (count_kmer.cpp:211, count_tnf.cpp:204): a
+// tally >= 10^6 arrives as e.g. 1.11493e+06 (KAT-5).  text_round6 reproduces printf("%g")'s decision in
+// integers - round to 6 significant digits, ties to even (every tally is an exactly representable integer, so
+// a tie is exactly half a unit) - and the kernel normalises the rounded values when `text_round` is set.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
 
 namespace pg {
 
+__host__ __device__ __forceinline__ unsigned long long text_round6(uint32_t v)
+{
+    if (v < 1000000u) return v;
+    const uint32_t q = v < 10000000u ? 10u : v < 100000000u ? 100u : v < 1000000000u ? 1000u : 10000u; // unit of the 6th digit
+    const uint32_t r = v % q, base = v - r;
+    const bool up = 2u * r > q || (2u * r == q && ((base / q) & 1u));
+    return (unsigned long long)base + (up ? q : 0u); // (64-bit: 4294967295 rounds to 4294970000)
+}
+
 __global__ void __launch_bounds__(256)
-normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, float* __restrict__ out, double* __restrict__ weights)
+normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, float* __restrict__ out, double* __restrict__ weights, int text_round)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
         const uint32_t* src = raw + r * dim;
         unsigned long long sum = 0;
-        uint32_t mx = 0;
+        unsigned long long mx = 0;
         for (int j = lane; j < dim; j += 32) {
-            uint32_t v = __ldg(src + j);
+            unsigned long long v = __ldg(src + j);
+            if (text_round) v = text_round6((uint32_t)v);
             sum += v;
             mx = max(mx, v);
         }
@@ -35,7 +51,11 @@ normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, f
         }
         const double norm = sum ? (double)sum : 1.0; // sklearn: zero norms are replaced by 1
         float* dst = out + r * dim;
-        for (int j = lane; j < dim; j += 32) dst[j] = (float)((double)__ldg(src + j) / norm);
+        for (int j = lane; j < dim; j += 32) {
+            unsigned long long v = __ldg(src + j);
+            if (text_round) v = text_round6((uint32_t)v);
+            dst[j] = (float)((double)v / norm);
+        }
         if (weights && lane == 0) {
             const double m = (double)mx / norm;
             weights[r] = m * m;

@@ -69,12 +69,13 @@ def slice_shard(shard: Shard, seq: np.ndarray, read_off: np.ndarray, read_flag: 
     """Views of one shard's arrays with offsets rebased to 0 (the layout pg_reads expects)."""
     off = np.ascontiguousarray(read_off[shard.read_lo:shard.read_hi + 1] - read_off[shard.read_lo])
     flag = read_flag[shard.read_lo:shard.read_hi]
-    keep = np.ascontiguousarray(group_keep[shard.group_lo:shard.group_hi])
-    if shard.n_groups == 0:  # an empty rank still owns one (empty, dropped) cloud locally
-        keep = np.zeros(1, dtype=np.uint8)
-    elif len(flag) and flag[-1] & PG_READ_CHANGE:
-        # the shard ends on a flush: locally that opens one more, empty cloud
-        keep = np.concatenate([keep, np.zeros(1, dtype=np.uint8)])
+    # Locally the shard has 1 + (its own PG_READ_CHANGE flags) clouds - that is what pg_featurize checks.  A shard that is
+    # not the last one ends on a flush, which locally opens one more, empty (dropped) cloud; the last shard's slice of
+    # group_keep already holds the trailing cloud of the stream; an empty rank owns one empty cloud.
+    n_local = 1 + int((np.asarray(flag) & PG_READ_CHANGE).sum())
+    keep = np.zeros(n_local, dtype=np.uint8)
+    own = np.asarray(group_keep[shard.group_lo:shard.group_hi], dtype=np.uint8)[:n_local]
+    keep[:len(own)] = own
     s = seq[shard.byte_lo:shard.byte_hi]
     q = qual[shard.byte_lo:shard.byte_hi] if qual is not None else None
     return s, off, flag, keep, q

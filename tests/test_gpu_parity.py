@@ -278,12 +278,101 @@ def test_normalize_bit_exact_vs_sklearn_semantics(oracle):
     abd[17] = 0
     abd[18, 3] = 4_000_000_000  # near the u32 ceiling
     tnf = rng.integers(0, 5000, size=(1000, 136)).astype(np.int64)
-    ctx = _ctx()
-    f = ctx.features_from_raw(abd, tnf)
-    a, t, w = f.normalized()
-    oa, ot, ow = oracle.data_init(abd, tnf)
-    assert a.dtype == np.float32 and w.dtype == np.float64
-    assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+    # tallies >= 10^6 reach the reference's Data.__init__ through 6-significant-digit text (KAT-5): exact ties included
+    abd[19, :6] = [1_000_005, 1_000_015, 12_345_650, 99_999_950, 1_114_935, 999_999]
+    tnf[20, :3] = [2_500_005_000, 1_114_934, 7]
+    for ctx in (_ctx(), _ctx(table_mode=_lib.PG_TABLE_NONE)):
+        f = ctx.features_from_raw(abd, tnf)
+        a, t, w = f.normalized()
+        oa, ot, ow = oracle.data_init(oracle.text_round(abd), oracle.text_round(tnf))
+        assert a.dtype == np.float32 and w.dtype == np.float64
+        assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+        ra, rt = f.raw()  # the raw tallies stay exact
+        assert np.array_equal(ra.view(np.uint32), abd.astype(np.uint32)) and np.array_equal(rt.view(np.uint32), tnf.astype(np.uint32))
+
+
+def test_tableless_ctx_only_normalises(tmp_path):
+    """Data.__init__ without device features builds a PG_TABLE_NONE ctx: no 2 GiB table, any vector_size, and everything
+    that needs the table fails loudly."""
+    from pangaea_b200 import Data
+
+    ctx = _ctx(table_mode=_lib.PG_TABLE_NONE, vector_size=20000)
+    rng = np.random.default_rng(1)
+    abd, tnf = rng.integers(0, 50, size=(7, 20000)), rng.integers(0, 50, size=(7, 136))
+    ds = Data(np.arange(7), abd, tnf)
+    assert ds.abd.shape == (7, 20000) and np.allclose(ds.abd.sum(axis=1), 1.0, atol=1e-4)
+    data = synth.generate(n_barcodes=3, mean_pairs=5, read_len=80, seed=1)
+    fq = _lib.Fastq(synth.write_interleaved(str(tmp_path / "i.fq"), data))
+    b = ctx.upload(fq.reads)
+    with pytest.raises(_lib.PgError, match="PG_TABLE_NONE"):
+        ctx.count(b)
+    with pytest.raises(_lib.PgError):
+        _ctx(window_size=2 ** 20, vector_size=4096)  # w * v > 2^31 - 1: a saturated counter could land in a bin
+
+
+@pytest.mark.parametrize("env", [{}, {"PG_COUNT_L2": "1"}, {"PG_FORCE_DIRECT": "1"}, {"PG_REGION_SLACK": "0.3"}])
+def test_counters_saturate_instead_of_wrapping(tmp_path, oracle, monkeypatch, env):
+    """A k-mer seen >= 2^31 times (poly-G at multi-billion-read scale): the dense counter stops at 2^31 - 1, whatever path
+    adds to it (shared-memory merge, overflow REDs, direct kernel), and the k-mer is dropped from the histogram exactly as
+    the reference drops the true count (count_kmer.cpp:90-92)."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    k = 15
+    rng = np.random.default_rng(5)
+    body = "".join(rng.choice(list("ACGT"), size=3000))
+    reads = []
+    for i in range(60):  # 60 pairs in one barcode; every read = 40 G (26 poly-G windows) + 60 genome bases
+        for _ in range(2):
+            o = int(rng.integers(0, len(body) - 60))
+            reads.append("G" * 40 + body[o:o + 60])
+    with open(tmp_path / "i.fq", "w") as f:
+        for i in range(0, len(reads), 2):
+            for r in reads[i:i + 2]:
+                f.write(f"@r{i} BX:Z:ACGTACGTACGTACGT-1\n{r}\n+\n{'I' * len(r)}\n")
+        for _ in range(2):  # a second barcode closes the first cloud
+            f.write(f"@z BX:Z:TTTTACGTACGTACGT-1\n{body[:100]}\n+\n{'I' * 100}\n")
+    fq = _lib.Fastq(str(tmp_path / "i.fq"))
+    ctx = _ctx(k=k, min_length=100)
+    polyg = oracle.encode("G" * k)
+    other = oracle.encode(body[100:100 + k])
+    near = 2 ** 31 - 1 - 1000                       # the batch adds 120 * 26 = 3120 > 1000 poly-G windows
+    ctx.table_set(np.array([polyg, other], np.uint64), np.array([near, 2 ** 31 - 1], np.uint32))
+    batch = ctx.upload(fq.reads)
+    ctx.count(batch)
+    want = oracle.Table()
+    for r in reads + [body[:100]] * 2:
+        want.count_read(r.encode() + b"\n", k)
+    assert want.get(oracle.canonical(polyg, k)) == 120 * 26
+    got = ctx.table_get(np.array([polyg, other], np.uint64))
+    assert got.tolist() == [2 ** 31 - 1, 2 ** 31 - 1], got
+    # every other counter is exact
+    keys, counts = ctx.table_export()
+    wk, wv = _oracle_table_arrays(want)
+    sel = ~np.isin(wk, [oracle.canonical(polyg, k), oracle.canonical(other, k)])
+    assert np.array_equal(keys[np.isin(keys, wk[sel])], wk[sel])
+    assert np.array_equal(counts[np.isin(keys, wk[sel])].astype(np.uint64), wv[sel])
+    # features: the saturated k-mers are beyond the histogram, like their true counts
+    feats = ctx.featurize(batch, fq.group_keep, fq.n_groups)
+    abd, _ = feats.raw()
+    want.set(oracle.canonical(polyg, k), near + 120 * 26)
+    want.set(oracle.canonical(other, k), 2 ** 31 - 1 + want.get(oracle.canonical(other, k)))
+    names, oabd, _ = oracle.featurize(str(tmp_path / "i.fq"), None, k=k, mlen=100, table=want)
+    assert _names(fq, feats) == list(names) and np.array_equal(abd, oabd)
+    # a table that holds zero-count markers cannot be counted into
+    ctx.table_clear()
+    ctx.table_set(np.array([polyg], np.uint64), np.array([0], np.uint32))
+    with pytest.raises(_lib.PgError, match="marker"):
+        ctx.count(batch)
+
+
+def test_table_clamp_before_a_sum_across_ranks():
+    ctx = _ctx(k=15)
+    keys = np.array([5, 6, 7], np.uint64)
+    ctx.table_set(keys, np.array([10, 2 ** 31 - 1, 300_000_000], np.uint32))
+    ctx.table_clamp((2 ** 31 - 1) // 8)
+    assert ctx.table_get(keys).tolist() == [10, (2 ** 31 - 1) // 8, (2 ** 31 - 1) // 8]
+    t = ctx.table_as_torch()
+    assert int((t.to("cuda").long() * 8).max()) < 2 ** 31   # the int32 sum of 8 such tables cannot reach bit 31
 
 
 def test_dlpack_zero_copy_to_torch(tmp_path):

@@ -104,3 +104,34 @@ def test_data_init_matches_sklearn(oracle):
     assert np.array_equal(t, normalize(tnf, "l1").astype(np.float32))
     assert np.array_equal(w, np.array([na[i].max() ** 2 for i in range(64)], dtype=np.float64))
     assert a.dtype == np.float32 and w.dtype == np.float64
+
+
+def test_text_round_matches_libc_printf_and_the_integer_rule(oracle):
+    """oracle.text_round (python "%.6g") == glibc printf("%.6g") == the integer rule csrc/normalize.cuh:text_round6 uses
+    (round to 6 significant digits, ties to even), on random tallies and on exact ties."""
+    import ctypes
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.snprintf.restype = ctypes.c_int
+    buf = ctypes.create_string_buffer(64)
+
+    def c_round(v):
+        libc.snprintf(buf, ctypes.c_size_t(64), b"%.6g", ctypes.c_double(float(v)))
+        return float(buf.value)
+
+    def int_rule(v):  # mirrors text_round6
+        if v < 1_000_000:
+            return v
+        q = 10 if v < 10 ** 7 else 100 if v < 10 ** 8 else 1000 if v < 10 ** 9 else 10000
+        r, base = v % q, v - v % q
+        up = 2 * r > q or (2 * r == q and (base // q) & 1)
+        return base + q if up else base
+
+    rng = np.random.default_rng(0)
+    vals = list(rng.integers(0, 2 ** 32, size=4000)) + list(rng.integers(999_990, 1_000_100, size=200))
+    vals += [1_000_005, 1_000_015, 1_000_025, 12_345_650, 12_345_750, 999_999, 1_000_000, 9_999_995, 9_999_985, 99_999_950, 99_999_850,
+             4_294_967_295, 4_294_965_000, 2_500_005_000, 1_114_930, 1_114_934, 1_114_935, 1_114_936]
+    for v in map(int, vals):
+        want = c_round(v)
+        assert float(int_rule(v)) == want, v
+        assert float(oracle.text_round(np.array([v], dtype=np.int64))[0]) == want, v

@@ -99,3 +99,26 @@ def test_plan_cuts_only_at_cloud_flushes():
     shards = plan_shards(np.array([0, 5, 9], np.int64), np.zeros(2, np.uint8), 4)
     assert [s.n_reads for s in shards] == [0, 0, 0, 2] and shards[-1].n_groups == 1
     assert [s.n_reads for s in plan_shards(np.zeros(1, np.int64), np.zeros(0, np.uint8), 2)] == [0, 0]
+
+
+@pytest.mark.parametrize("flags", [[0, 1, 0, 0, 0, 1, 0, 1], [0, 1, 0, 1], [0, 0, 0, 1], [0, 1, 0, 0], [0, 0]])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_slice_keep_length_matches_local_clouds(flags, world):
+    """pg_featurize insists on n_groups == 1 + local change flags; the stream may END on a flagged read (the file's last
+    barcode has exactly one pair), in which case the trailing cloud is empty and already part of group_keep."""
+    flag = np.array(flags, dtype=np.uint8)
+    n = len(flag)
+    off = np.arange(n + 1, dtype=np.int64) * 11
+    seq = np.zeros(int(off[-1]), dtype=np.uint8)
+    n_groups = 1 + int(flag.sum())
+    keep = (np.arange(n_groups) % 2).astype(np.uint8)       # recognisable pattern
+    seen = []
+    for shard in plan_shards(off, flag, world):
+        s, soff, sflag, skeep, _ = slice_shard(shard, seq, off, flag, keep)
+        assert len(skeep) == 1 + int((sflag & 1).sum()), (shard, skeep)
+        assert len(soff) == len(sflag) + 1 and (len(s) == soff[-1] if len(sflag) else len(s) == 0)
+        own = shard.group_hi - shard.group_lo
+        assert list(skeep[:own]) == list(keep[shard.group_lo:shard.group_hi][:len(skeep)])
+        assert not skeep[own:].any(), "the cloud a flush opens locally is empty and dropped"
+        seen.append(own)
+    assert sum(seen) == n_groups
