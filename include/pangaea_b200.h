@@ -95,6 +95,8 @@ int pg_device_count(void);
 /* tnf_k -> number of canonical columns (136 for 4); count_tnf.cpp:138-164 */
 int pg_tnf_dim(int tnf_k);
 int pg_synchronize(pg_ctx* ctx);
+/* free / total device memory as the driver reports it, plus what this ctx holds idle in its caches (reusable by it) */
+int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
 /* the cudaStream_t every launch of this ctx goes to (for CUDA-event timing by the caller) */
 void* pg_stream(pg_ctx* ctx);
 
@@ -104,6 +106,12 @@ int pg_batch_upload(pg_ctx* ctx, const pg_reads* host, pg_batch** out);
 /* adopt device pointers without copying (pointers must stay valid; seq 16-byte aligned) and pack */
 int pg_batch_adopt(pg_ctx* ctx, const pg_reads* dev, pg_batch** out);
 void pg_batch_free(pg_ctx* ctx, pg_batch* b);
+/* one batch of a stream: pg_batch_upload + pg_count2 with the copy overlapped chunk by chunk; the table is NOT cleared */
+int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep_partition, pg_batch** out);
+/* release the ASCII bases (and a kept partition): the 2-bit stream, masks and read offsets - 0.5 B per base + 9 B per
+ * read - stay, which is all pg_featurize needs.  Lets the batches of a file larger than HBM's ASCII capacity wait
+ * on the device for the featurize pass. */
+int pg_batch_compact(pg_ctx* ctx, pg_batch* b);
 int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE flags */
 
 /* ---- step 1a: global canonical k-mer counts --------------------------------- */
@@ -113,6 +121,8 @@ int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE fl
  * pg_featurize needs too, so - memory permitting - it is KEPT in the batch (about 0.75 KB per read pair of 2x100 bp,
  * from a buffer the ctx reuses) until pg_batch_free; pg_featurize of the same batch then skips its own partition. */
 int pg_count(pg_ctx* ctx, pg_batch* b);
+/* keep_partition = 0: do not keep the partition (a stream of batches is counted first and featurized later) */
+int pg_count2(pg_ctx* ctx, pg_batch* b, int keep_partition);
 int pg_table_clear(pg_ctx* ctx);
 /* kmer2frequency[key] = count (count_kmer.cpp:166): assignment, keys in the reference's
  * canonical form or not (re-canonicalised).  A key set with count 0 is PRESENT with
@@ -160,6 +170,10 @@ int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, float* abd_ou
  * the `Data(barcodes, abd, tnf)` entry when the matrices come from load_features() */
 int pg_features_from_raw(pg_ctx* ctx, const uint32_t* abd, const uint32_t* tnf, int64_t rows, int32_t abd_dim, int32_t tnf_dim, pg_features** out);
 
+/* rows of consecutive batches as one feature set (device-to-device copies; the parts stay valid).  Its row_groups are
+ * the parts' batch-local cloud indices. */
+int pg_features_concat(pg_ctx* ctx, pg_features* const* parts, int32_t n_parts, pg_features** out);
+
 /* zero-copy hand-off: which = 0 abd_raw(i32) 1 tnf_raw(i32) 2 abd(f32) 3 tnf(f32) 4 weights(f64).
  * Returns a DLManagedTensor* (DLPack v0.8 layout) whose deleter releases a reference
  * on the feature set; wrap it in a PyCapsule named "dltensor". */
@@ -174,13 +188,34 @@ int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint8_t* group_
 /* ---- host FASTQ reader (replaces the getline loops, count_kmer.cpp:181-282,
  *      and getBarcode, count_kmer.cpp:25-53) ------------------------------------ */
 typedef struct pg_fastq pg_fastq;
-/* path2 == NULL: interleaved (-i), else paired (-1/-2).  Plain text or gzip. */
-int pg_fastq_parse(const char* path1, const char* path2, int want_qual, pg_fastq** out);
+enum { PG_FQ_QUAL = 1,    /* keep the quality lines (needed when pg_params.min_qual_char != 0) */
+       PG_FQ_PINNED = 2   /* batch buffers in page-locked host memory (create the pg_ctx first: this touches the CUDA device) */ };
+/* the whole input as ONE batch.  path2 == NULL: interleaved (-i), else paired (-1/-2).  Plain text or gzip. */
+int pg_fastq_parse(const char* path1, const char* path2, int flags, pg_fastq** out);
 void pg_fastq_free(pg_fastq* fq);
 void pg_fastq_reads(const pg_fastq* fq, pg_reads* out);      /* host pointers owned by fq */
 int64_t pg_fastq_n_groups(const pg_fastq* fq);
 const uint8_t* pg_fastq_group_keep(const pg_fastq* fq);       /* n_groups bytes */
 const char* pg_fastq_group_label(const pg_fastq* fq, int64_t g);
+/* all labels at once: concatenated into buf (no terminators), offsets[n_groups + 1].  Returns the bytes needed; nothing
+ * is written when cap is smaller (call with buf = NULL to size). */
+int64_t pg_fastq_group_labels(const pg_fastq* fq, char* buf, int64_t cap, int64_t* offsets);
+
+/* The same reader as a STREAM of batches - the reference handles files of any size one cloud at a time
+ * (count_kmer.cpp:236-282); here the unit is a batch of about target_seq_bytes that ends where the reference would
+ * flush a cloud (or inside a cloud labelled "", which is dropped whole).  read_type and last_barcode are carried from
+ * batch to batch; label 0 of a batch is the label of the cloud that is open when the batch starts.  Feed every batch
+ * to pg_count, then featurize batch by batch: rows of consecutive batches concatenate to the reference's row order.
+ * byte_lo / byte_hi (plain-text interleaved files only; 0 / -1 = the whole file): one rank of a multi-GPU run reads
+ * the clouds that START in its byte range; lines_before_lo = number of '\n' in [0, byte_lo) (pg_fastq_count_lines,
+ * summed over the lower ranks) - record boundaries are line numbers 0 mod 8. */
+typedef struct pg_fastq_stream pg_fastq_stream;
+int pg_fastq_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int64_t* n_newlines);
+int pg_fastq_stream_open(const char* path1, const char* path2, int flags, int64_t byte_lo, int64_t byte_hi, int64_t lines_before_lo,
+                         pg_fastq_stream** out);
+/* *out = NULL at the end of the stream; target_seq_bytes <= 0: everything that is left */
+int pg_fastq_stream_next(pg_fastq_stream* s, int64_t target_seq_bytes, pg_fastq** out);
+void pg_fastq_stream_close(pg_fastq_stream* s);
 
 /* ---- synthetic reads on device (bench input) --------------------- */
 /* fills DEVICE buffers shaped like a pg_reads batch: n_pairs pairs of 2 x read_len,
@@ -189,6 +224,13 @@ const char* pg_fastq_group_label(const pg_fastq* fq, int64_t g);
 int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
                       const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
                       double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag);
+
+/* the same with a global index for the batch's first barcode and first pair: batches / ranks that share `seed` draw
+ * different clouds from the same community of genomes */
+int pg_synth_generate2(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
+                       const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
+                       double n_rate, uint64_t seed, int64_t bc_base, int64_t pair_base, uint8_t* d_seq, int64_t* d_read_off,
+                       uint8_t* d_read_flag);
 
 /* ---- instrumentation -------------------------------------------------------- */
 /* device time (ms, CUDA events on the ctx stream) and launch count of the kernels run

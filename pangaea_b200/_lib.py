@@ -17,6 +17,7 @@ PG_READ_CHANGE, PG_READ_NOFEAT = 1, 2
 PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH, PG_TABLE_NONE = 0, 1, 2, 3
 T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL, T_COUNT_SCATTER, T_FEAT_SCATTER, T_TNF, T_COUNT_SPLIT = range(10)
 ABD_RAW, TNF_RAW, ABD, TNF, WEIGHTS = range(5)
+PG_FQ_QUAL, PG_FQ_PINNED = 1, 2
 
 
 class PgError(RuntimeError):
@@ -57,6 +58,10 @@ SIGNATURES = {
     "pg_batch_free": (None, [_vp, _vp]),
     "pg_batch_n_groups": (_i64, [_vp]),
     "pg_count": (_int, [_vp, _vp]),
+    "pg_count2": (_int, [_vp, _vp, _int]),
+    "pg_batch_upload_count": (_int, [_vp, _P(pg_reads), _int, _P(_vp)]),
+    "pg_batch_compact": (_int, [_vp, _vp]),
+    "pg_features_concat": (_int, [_vp, _P(_vp), _i32, _P(_vp)]),
     "pg_table_clear": (_int, [_vp]),
     "pg_table_set": (_int, [_vp, _vp, _vp, _i64]),
     "pg_table_get": (_int, [_vp, _vp, _vp, _i64]),
@@ -79,12 +84,19 @@ SIGNATURES = {
     "pg_features_device_ptr": (_vp, [_vp, _int]),
     "pg_extract_features": (_int, [_vp, _P(pg_reads), _vp, _i64, _P(_vp)]),
     "pg_fastq_parse": (_int, [C.c_char_p, C.c_char_p, _int, _P(_vp)]),
+    "pg_fastq_count_lines": (_int, [C.c_char_p, _i64, _i64, _P(_i64)]),
+    "pg_fastq_stream_open": (_int, [C.c_char_p, C.c_char_p, _int, _i64, _i64, _i64, _P(_vp)]),
+    "pg_fastq_stream_next": (_int, [_vp, _i64, _P(_vp)]),
+    "pg_fastq_stream_close": (None, [_vp]),
     "pg_fastq_free": (None, [_vp]),
     "pg_fastq_reads": (None, [_vp, _P(pg_reads)]),
     "pg_fastq_n_groups": (_i64, [_vp]),
     "pg_fastq_group_keep": (_vp, [_vp]),
     "pg_fastq_group_label": (C.c_char_p, [_vp, _i64]),
+    "pg_fastq_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
+    "pg_mem_info": (_int, [_vp, _P(_i64), _P(_i64)]),
     "pg_synth_generate": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _vp, _vp, _vp]),
+    "pg_synth_generate2": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _i64, _i64, _vp, _vp, _vp]),
     "pg_timing_reset": (_int, [_vp]),
     "pg_timing_get": (_int, [_vp, _int, _P(C.c_double), _P(_i64)]),
 }
@@ -127,14 +139,18 @@ def make_reads(seq, read_off, read_flag, qual=None, n_reads=None, n_bytes=None) 
 
 
 class Fastq:
-    """Host FASTQ reader (csrc/fastq.cpp): replaces the getline loops of count_kmer.cpp:181-282."""
+    """One batch of the host FASTQ reader (csrc/fastq.cpp): replaces the getline loops of count_kmer.cpp:181-282.
+    ``Fastq(path)`` parses the whole input as one batch; ``FastqStream`` yields batches."""
 
-    def __init__(self, path1, path2=None, want_qual=False):
-        h = _vp()
-        rc = lib().pg_fastq_parse(os.fsencode(path1), os.fsencode(path2) if path2 else None, int(want_qual), C.byref(h))
-        if rc != 0:
-            raise PgError(rc, f"cannot read {path1!r}" + (f" / {path2!r}" if path2 else ""))
-        self.h = h
+    def __init__(self, path1=None, path2=None, want_qual=False, pinned=False, handle=None):
+        if handle is None:
+            h = _vp()
+            flags = (PG_FQ_QUAL if want_qual else 0) | (PG_FQ_PINNED if pinned else 0)
+            rc = lib().pg_fastq_parse(os.fsencode(path1), os.fsencode(path2) if path2 else None, flags, C.byref(h))
+            if rc != 0:
+                raise PgError(rc, f"cannot read {path1!r}" + (f" / {path2!r}" if path2 else ""))
+            handle = h
+        self.h = handle
         self.reads = pg_reads()
         lib().pg_fastq_reads(self.h, C.byref(self.reads))
         self.n_groups = int(lib().pg_fastq_n_groups(self.h))
@@ -142,6 +158,16 @@ class Fastq:
 
     def label(self, g: int) -> str:
         return lib().pg_fastq_group_label(self.h, g).decode("utf-8", "surrogateescape")
+
+    def labels(self):
+        """all cloud labels as a list of str (one bulk call instead of n_groups ctypes calls)"""
+        need = int(lib().pg_fastq_group_labels(self.h, None, 0, None))
+        buf = np.empty(max(need, 1), dtype=np.uint8)
+        off = np.empty(self.n_groups + 1, dtype=np.int64)
+        lib().pg_fastq_group_labels(self.h, buf.ctypes.data, need, off.ctypes.data)
+        blob = buf[:need].tobytes()
+        o = off.tolist()
+        return [blob[o[g]:o[g + 1]].decode("utf-8", "surrogateescape") for g in range(self.n_groups)]
 
     def arrays(self):
         """numpy views (seq, read_off, read_flag, keep) - valid while self lives."""
@@ -153,6 +179,50 @@ class Fastq:
     def close(self):
         if getattr(self, "h", None):
             lib().pg_fastq_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def count_lines(path, byte_lo=0, byte_hi=-1) -> int:
+    n = _i64()
+    rc = lib().pg_fastq_count_lines(os.fsencode(path), int(byte_lo), int(byte_hi), C.byref(n))
+    if rc != 0:
+        raise PgError(rc, f"cannot read {path!r}")
+    return int(n.value)
+
+
+class FastqStream:
+    """Batches of about ``target_seq_bytes`` sequence bytes, each ending at a cloud flush (pg_fastq_stream_*).
+    ``byte_lo`` / ``byte_hi`` / ``lines_before_lo``: this rank's byte range of a plain-text interleaved file."""
+
+    def __init__(self, path1, path2=None, want_qual=False, pinned=False, target_seq_bytes=0, byte_lo=0, byte_hi=-1, lines_before_lo=0):
+        h = _vp()
+        flags = (PG_FQ_QUAL if want_qual else 0) | (PG_FQ_PINNED if pinned else 0)
+        rc = lib().pg_fastq_stream_open(os.fsencode(path1), os.fsencode(path2) if path2 else None, flags, int(byte_lo), int(byte_hi),
+                                        int(lines_before_lo), C.byref(h))
+        if rc != 0:
+            raise PgError(rc, f"cannot read {path1!r}" + (f" / {path2!r}" if path2 else ""))
+        self.h, self.target, self.path1 = h, int(target_seq_bytes), path1
+
+    def next(self):
+        """-> Fastq, or None at the end of the stream (ctypes releases the GIL: call it from a feeder thread)."""
+        out = _vp()
+        rc = lib().pg_fastq_stream_next(self.h, self.target, C.byref(out))
+        if rc != 0:
+            raise PgError(rc, f"error while reading {self.path1!r} (I/O error, truncated gzip stream or out of memory)")
+        return Fastq(handle=out) if out.value else None
+
+    def __iter__(self):
+        while True:
+            fq = self.next()
+            if fq is None:
+                return
+            yield fq
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pg_fastq_stream_close(self.h)
             self.h = None
 
     __del__ = close
@@ -221,6 +291,12 @@ class Batch:
     def __init__(self, ctx: "Context", handle, keepalive=None):
         self.ctx, self.h, self._keep = ctx, handle, keepalive
 
+    def compact(self):
+        """drop the ASCII bases (and a kept partition); the packed stream stays for pg_featurize"""
+        self.ctx._ck(lib().pg_batch_compact(self.ctx.h, self.h))
+        self._keep = None
+        return self
+
     def free(self):
         if getattr(self, "h", None) and self.ctx.h:
             lib().pg_batch_free(self.ctx.h, self.h)
@@ -269,6 +345,12 @@ class Context:
     def synchronize(self):
         self._ck(lib().pg_synchronize(self.h))
 
+    def mem_info(self):
+        """(bytes this ctx can still get, total device bytes)"""
+        f, t = _i64(), _i64()
+        self._ck(lib().pg_mem_info(self.h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
     # ---- batches -------------------------------------------------------------
     def upload(self, reads: pg_reads, keepalive=None) -> Batch:
         h = _vp()
@@ -281,8 +363,20 @@ class Context:
         return Batch(self, h, keepalive)
 
     # ---- table ---------------------------------------------------------------
-    def count(self, batch: Batch):
-        self._ck(lib().pg_count(self.h, batch.h))
+    def count(self, batch: Batch, keep_partition=True):
+        self._ck(lib().pg_count2(self.h, batch.h, int(keep_partition)))
+
+    def upload_count(self, reads: pg_reads, keep_partition=False, keepalive=None) -> Batch:
+        """one batch of a stream: pipelined upload + count; the table is not cleared"""
+        h = _vp()
+        self._ck(lib().pg_batch_upload_count(self.h, C.byref(reads), int(keep_partition), C.byref(h)))
+        return Batch(self, h, keepalive)
+
+    def concat_features(self, parts) -> "Features":
+        arr = (_vp * len(parts))(*[p.h for p in parts])
+        h = _vp()
+        self._ck(lib().pg_features_concat(self.h, arr, len(parts), C.byref(h)))
+        return Features(self, h)
 
     def table_clear(self):
         self._ck(lib().pg_table_clear(self.h))

@@ -435,6 +435,19 @@ extern "C" int pg_synchronize(pg_ctx* ctx)
 
 extern "C" void* pg_stream(pg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+static size_t available_bytes(pg_ctx* ctx);
+
+extern "C" int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes)
+{
+    if (!ctx || !free_bytes || !total_bytes) return fail(ctx, PG_ERR_INVALID, "pg_mem_info: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    *free_bytes = (int64_t)(available_bytes(ctx) + ctx->big.free_bytes + ctx->ws_stash.bytes);
+    *total_bytes = (int64_t)t;
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // timing
 // ---------------------------------------------------------------------------
@@ -726,14 +739,14 @@ static BucketGeom padded_geom(BucketGeom geo) // feature-format runs are padded 
 // One partition for both passes (bucket.cuh: kScatterShared) when the batch allows it: no quality filter (feature
 // windows must be a subset of the counted ones), every cloud >= 64 bytes, and room to keep the entries until
 // pg_featurize.  Otherwise each pass partitions for itself.
-static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed = true)
+static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed = true, bool keep = true)
 {
     const int64_t n_words = b->n_words;
     P.two_level = !ctx->count_l2;
     P.seg_words = std::max<int64_t>(1, std::min<int64_t>(n_words, P.two_level ? ctx->count_seg_words : ctx->seg_words));
     P.geo = bucket_geom(ctx, P.seg_words);
     P.shared = false;
-    if (P.two_level && !ctx->no_shared && !ctx->p.min_qual_char && b->stash.empty() && b->read_flag && b->read_off && n_words > 0) {
+    if (P.two_level && keep && !ctx->no_shared && !ctx->p.min_qual_char && b->stash.empty() && b->read_flag && b->read_off && n_words > 0) {
         int rc = group_stage_a(ctx, b, true, packed);
         if (rc) return rc;
         const BucketGeom pg = padded_geom(P.geo);
@@ -842,7 +855,7 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
             sub_reset_kernel<<<16, 1024, 0, ctx->stream>>>(P.ss, P.sg);
             bucket_split_kernel<<<P.split_grid, kSplitThreads, sizeof(SplitSmem), ctx->stream>>>(Q.entries, P.geo, ctx->d_bucket, P.sg, P.ss, P.entries2, ctx->counts, ctx->d_sat);
         }
-        Timed t(ctx, T_COUNT, 2);
+        Timed t(ctx, T_COUNT, 3);
         sub_items_kernel<<<1, 1024, 0, ctx->stream>>>(P.ss, P.sg);
         sub_apply_kernel<<<ctx->sm_count, kSubApplyThreads, kSubWords * 4 + 16, ctx->stream>>>(P.entries2, P.sg, P.ss, ctx->counts, ctx->d_sat);
         CK(saturate_if_flagged(ctx, true));
@@ -855,17 +868,19 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
     return PG_OK;
 }
 
-static int count_bucketed(pg_ctx* ctx, pg_batch* b)
+static int count_bucketed(pg_ctx* ctx, pg_batch* b, bool keep)
 {
     CountPlan P;
     free_stash(ctx, b); // counting a batch again: its old entries are stale
-    int rc = count_plan_init(ctx, b, P);
+    int rc = count_plan_init(ctx, b, P, true, keep);
     for (int64_t w0 = 0; !rc && w0 < b->n_words; w0 += P.seg_words) rc = count_segment(ctx, P, b, w0, std::min(b->n_words, w0 + P.seg_words));
     count_plan_free(ctx, P);
     return rc;
 }
 
-extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
+extern "C" int pg_count(pg_ctx* ctx, pg_batch* b) { return pg_count2(ctx, b, 1); }
+
+extern "C" int pg_count2(pg_ctx* ctx, pg_batch* b, int keep_partition)
 {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
@@ -874,7 +889,7 @@ extern "C" int pg_count(pg_ctx* ctx, pg_batch* b)
     int rc = ensure_table(ctx, b->n_bytes);
     if (rc) return rc;
     if (b->n_words && use_buckets(ctx)) {
-        rc = count_bucketed(ctx, b);
+        rc = count_bucketed(ctx, b, keep_partition != 0);
         if (rc) return rc;
     } else if (b->n_words) {
         // launches of < 2^31 windows, each followed by the (gated) clamp: a dense counter cannot wrap (table.cuh: saturation)
@@ -1483,7 +1498,7 @@ extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
 // compute stream packs chunk c and counts chunk c - 1 (a window of chunk c - 1 may end in the first
 // words of chunk c), so the count pass hides behind the copy.  Featurize needs the complete table
 // and starts when the last chunk is counted.
-static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
+static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch** out, bool keep = true)
 {
     pg_batch* b = nullptr;
     int rc = alloc_batch(ctx, h, &b);
@@ -1515,7 +1530,7 @@ static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch**
     CKB(copy_chunk(0));
     CKB(cudaStreamWaitEvent(ctx->stream, ev_meta, 0));
     CKB(cudaStreamWaitEvent(ctx->stream, ev, 0));      // (chunk 0's record; captured now, before the event is re-recorded)
-    rc = count_plan_init(ctx, b, P, false);            // derives the cloud structure (host waits for the flags only)
+    rc = count_plan_init(ctx, b, P, false, keep);      // derives the cloud structure (host waits for the flags only)
     if (rc) return bail(rc);
     if (P.seg_words != seg) return bail(fail(ctx, PG_ERR_STATE, "pipelined upload: segment size mismatch"));
     for (int64_t c = 0; c < n_chunks; ++c) {
@@ -1535,6 +1550,74 @@ static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch**
     ctx->pool.push_back(ev); ctx->pool.push_back(ev_meta);
     ctx->counted = true;
     *out = b;
+    return PG_OK;
+}
+
+// upload + count of one batch of a stream; the table is NOT cleared (batches add up)
+extern "C" int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep_partition, pg_batch** out)
+{
+    if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
+    if (ctx->zero_markers) return fail(ctx, PG_ERR_STATE, "pg_batch_upload_count: the table holds zero-count markers from pg_table_set - call pg_table_clear first");
+    int rc = ensure_table(ctx, host ? host->n_bytes : 0);
+    if (rc) return rc;
+    pg_batch* b = nullptr;
+    if (use_buckets(ctx) && host && host->n_reads > 0 && host->n_bytes >= (1 << 20)) {
+        rc = check_host_batch(ctx, host);
+        if (!rc) rc = upload_and_count_pipelined(ctx, host, &b, keep_partition != 0);
+        if (rc) return rc;
+    } else {
+        rc = pg_batch_upload(ctx, host, &b);
+        if (rc) return rc;
+        rc = pg_count2(ctx, b, keep_partition);
+        if (rc) { pg_batch_free(ctx, b); return rc; }
+    }
+    *out = b;
+    return PG_OK;
+}
+
+extern "C" int pg_batch_compact(pg_ctx* ctx, pg_batch* b)
+{
+    if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->p.device));
+    if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); }
+    b->seq = b->qual = nullptr; // (an adopted batch: the caller may release its buffers now)
+    free_stash(ctx, b);
+    return PG_OK;
+}
+
+extern "C" int pg_features_concat(pg_ctx* ctx, pg_features* const* parts, int32_t n_parts, pg_features** out)
+{
+    if (!ctx || !out || n_parts < 0 || (n_parts && !parts)) return fail(ctx, PG_ERR_INVALID, "pg_features_concat: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->p.device));
+    int64_t rows = 0;
+    int32_t vs = ctx->p.vector_size, td = ctx->td;
+    for (int i = 0; i < n_parts; ++i) {
+        if (!parts[i]) return fail(ctx, PG_ERR_INVALID, "pg_features_concat: null part");
+        if (i == 0) { vs = parts[i]->vs; td = parts[i]->td; }
+        if (parts[i]->vs != vs || parts[i]->td != td) return fail(ctx, PG_ERR_INVALID, "pg_features_concat: parts differ in shape");
+        rows += parts[i]->rows;
+    }
+    pg_features* f = new pg_features();
+    f->device = ctx->p.device; f->rows = rows; f->vs = vs; f->td = td;
+    cudaError_t e = dmalloc(ctx, &f->abd_raw, (size_t)rows * vs);
+    if (e == cudaSuccess) e = dmalloc(ctx, &f->tnf_raw, (size_t)rows * td);
+    if (e == cudaSuccess) e = dmalloc(ctx, &f->group_of_row, (size_t)rows);
+    int64_t at = 0;
+    for (int i = 0; i < n_parts && e == cudaSuccess; ++i) {
+        const pg_features* q = parts[i];
+        if (!q->rows) continue;
+        e = cudaMemcpyAsync(f->abd_raw + at * vs, q->abd_raw, (size_t)q->rows * vs * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->tnf_raw + at * td, q->tnf_raw, (size_t)q->rows * td * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->group_of_row + at, q->group_of_row, (size_t)q->rows * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        at += q->rows;
+    }
+    if (e != cudaSuccess) { pg_features_free(ctx, f); return fail(ctx, PG_ERR_CUDA, std::string("pg_features_concat: ") + cudaGetErrorString(e)); }
+    *out = f;
     return PG_OK;
 }
 
@@ -1566,9 +1649,10 @@ extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint
 // ---------------------------------------------------------------------------
 // synthetic reads (bench input)
 // ---------------------------------------------------------------------------
-extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
-                                 const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
-                                 double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag)
+extern "C" int pg_synth_generate2(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
+                                  const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
+                                  double n_rate, uint64_t seed, int64_t bc_base, int64_t pair_base, uint8_t* d_seq, int64_t* d_read_off,
+                                  uint8_t* d_read_flag)
 {
     if (!ctx || n_pairs < 0 || read_len < 1 || n_barcodes < 1 || !d_bc_start || !d_bc_genome || !d_seq || !d_read_off || !d_read_flag)
         return fail(ctx, PG_ERR_INVALID, "pg_synth_generate: bad argument");
@@ -1579,10 +1663,18 @@ extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len,
     S.genome_len = genome_len; S.frag_len = frag_len; S.insert = insert;
     S.sub_thresh = (uint32_t)std::min(4294967295.0, sub_rate * 4294967296.0);
     S.n_thresh = (uint32_t)std::min(4294967295.0, n_rate * 4294967296.0);
-    S.seed = seed;
+    S.seed = seed; S.bc_base = bc_base; S.pair_base = pair_base;
     synth_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(S, d_seq, d_read_off, d_read_flag);
     synth_flags_kernel<<<(int)((n_barcodes + 255) / 256), 256, 0, ctx->stream>>>(S, d_read_flag);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
+}
+
+extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
+                                 const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
+                                 double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag)
+{
+    return pg_synth_generate2(ctx, n_pairs, read_len, n_barcodes, d_bc_start, d_bc_genome, genome_len, frag_len, insert, sub_rate, n_rate, seed, 0, 0,
+                              d_seq, d_read_off, d_read_flag);
 }

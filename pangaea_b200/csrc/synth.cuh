@@ -22,6 +22,8 @@ struct SynthParams {
     int32_t frag_len, insert;
     uint32_t sub_thresh, n_thresh; // rate * 2^32
     uint64_t seed;
+    int64_t bc_base, pair_base; // global index of this batch's first barcode / pair: batches and ranks that share a seed draw
+                                // different clouds from the SAME community of genomes
 };
 
 __device__ __forceinline__ uint32_t synth_base(uint64_t seed, int32_t genome, int64_t pos)
@@ -56,15 +58,15 @@ synth_kernel(const SynthParams S, uint8_t* __restrict__ seq, int64_t* __restrict
                         if (__ldg(S.bc_start + mid) <= pair) lo = mid; else hi = mid;
                     }
                     genome = __ldg(S.bc_genome + lo);
-                    const uint64_t hb = mix64(S.seed ^ 0x9E3779B97F4A7C15ull ^ (uint64_t)lo);
-                    const uint64_t hp = mix64(S.seed ^ 0xD1B54A32D192ED03ull ^ (uint64_t)pair);
+                    const uint64_t hb = mix64(S.seed ^ 0x9E3779B97F4A7C15ull ^ (uint64_t)(lo + S.bc_base));
+                    const uint64_t hp = mix64(S.seed ^ 0xD1B54A32D192ED03ull ^ (uint64_t)(pair + S.pair_base));
                     const int64_t frag = (int64_t)(hb % (uint64_t)(S.genome_len - S.frag_len + 1));
                     start = frag + (int64_t)(hp % (uint64_t)(S.frag_len - S.insert + 1));
                 }
                 uint32_t code;
                 if ((r & 1) == 0) code = synth_base(S.seed, genome, start + i);
                 else code = 3u - synth_base(S.seed, genome, start + S.insert - 1 - i); // complement in ACGT order
-                const uint64_t e = mix64(S.seed ^ 0xA0761D6478BD642Full ^ (uint64_t)p);
+                const uint64_t e = mix64(S.seed ^ 0xA0761D6478BD642Full ^ (uint64_t)(p + S.pair_base * 2 * rl));
                 if ((uint32_t)e < S.sub_thresh) code = (uint32_t)(e >> 40) & 3u;
                 ch = letters[code];
                 if ((uint32_t)(e >> 32) < S.n_thresh) ch = 'N';

@@ -43,6 +43,58 @@ def extract_features_sharded(ctx: "_lib.Context", seq, read_off, read_flag, grou
     return feats, shard
 
 
+def extract_features_from_file(ctx: "_lib.Context", path, rank=None, world=None, group=None, want_qual=False, batch_seq_bytes=None):
+    """Whole path for this rank's BYTE RANGE of a plain-text interleaved FASTQ: the file is parsed once in aggregate.
+
+    Every rank counts the newlines of its 1/world of the file (pg_fastq_count_lines); the counts are all-gathered - the only
+    host-side exchange - so each rank knows the line number at its cut and can snap to a record boundary and then to the
+    next cloud flush (csrc/fastq.cpp: align_start; the rank before ends at the same point).  Each rank then streams its
+    range through the GPU (pangaea_b200/stream.py); between the count pass and the featurize pass the dense tables are
+    summed with one all-reduce.  Rows stay sharded: rank order == file order.
+    Returns (names list[str], Features).  Collective: every rank must call it."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from . import stream as stream_mod
+
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    size = os.path.getsize(path)
+    lo, hi = size * rank // world, size * (rank + 1) // world
+    before = 0
+    if world > 1:
+        mine = torch.tensor([_lib.count_lines(path, lo, hi)], dtype=torch.int64, device=f"cuda:{ctx.params.device}" if dist.get_backend(group) == "nccl" else "cpu")
+        counts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(counts, mine, group=group)
+        before = int(sum(int(c) for c in counts[:rank]))
+    table = ctx.table_as_torch() if world > 1 else None
+
+    def reduce_table():
+        if world > 1:
+            ctx.all_reduce_table(table, group=group)
+
+    def open_stream():
+        return _lib.FastqStream(path, None, want_qual=want_qual, pinned=True, target_seq_bytes=batch_seq_bytes or stream_mod.DEFAULT_BATCH_SEQ_BYTES,
+                                byte_lo=lo, byte_hi=hi if rank + 1 < world else -1, lines_before_lo=before)
+
+    return stream_mod.extract_features_streaming(ctx, open_stream, reduce_table=reduce_table)
+
+
+def gather_rows_named(names, feats: "_lib.Features", group=None):
+    """Rank 0 gets (names, abundance int32, tnf int32) of all ranks in rank order (= file order); other ranks get None."""
+    import torch.distributed as dist
+
+    abd, tnf = feats.raw()
+    world = dist.get_world_size(group)
+    out = [None] * world if dist.get_rank(group) == 0 else None
+    dist.gather_object((list(names), abd, tnf), out, dst=0, group=group)
+    if out is None:
+        return None
+    return (np.array(sum((p[0] for p in out), []), dtype=object), np.concatenate([p[1] for p in out]), np.concatenate([p[2] for p in out]))
+
+
 def gather_rows(feats: "_lib.Features", shard, labels_of_group, group=None):
     """Rank 0 gets (names, abundance int32, tnf int32) for ALL clouds in file order; other
     ranks get None.  labels_of_group: callable global cloud index -> label."""

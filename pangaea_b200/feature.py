@@ -15,6 +15,7 @@ import os
 import numpy as np
 
 from . import _lib
+from . import stream as stream_mod
 
 
 def _reference_text_rounding(m: np.ndarray) -> np.ndarray:
@@ -45,7 +46,7 @@ def write_reference_csv(path, names, matrix):
 
 
 class Feature:
-    def __init__(self, args, script_path=None, device=0):
+    def __init__(self, args, script_path=None, device=0, batch_seq_bytes=None):
         # /root/reference/src/feature.py:12-26
         self.args = args
         self.tnf_k = str(args.tnf_kmer)
@@ -59,6 +60,9 @@ class Feature:
         os.makedirs(self.feature_dir, exist_ok=True)
         self.features = None  # device-resident matrices of the last extract_features()
         self.timing = {}
+        # the input is streamed through the GPU in batches of about this many sequence bytes (pangaea_b200/stream.py), so a
+        # file of any size works - like the reference, which holds one cloud at a time (count_kmer.cpp:236-282)
+        self.batch_seq_bytes = int(batch_seq_bytes or os.environ.get("PG_BATCH_SEQ_BYTES", 0) or stream_mod.DEFAULT_BATCH_SEQ_BYTES)
 
     # -- file names of the reference's cache artefacts (feature.py:42-44,68-71,126-127)
     def _abd_pkl(self):
@@ -91,18 +95,17 @@ class Feature:
             names, abundance, tnf = self.load_features()
         else:
             path1, path2, min_qual = self._inputs()
-            fq = _lib.Fastq(path1, path2, want_qual=bool(min_qual))
             ctx = _lib.Context(device=self.device, k=int(self.kmer), tnf_k=int(self.tnf_k), window_size=int(self.ws),
                                vector_size=int(self.vs), min_length=int(self.minl), min_qual_char=min_qual)
-            feats = ctx.extract_features(fq.reads, fq.group_keep, fq.n_groups)
-            names = np.array([fq.label(int(g)) for g in feats.row_groups()], dtype=object)
+            names, feats = stream_mod.extract_features_streaming(
+                ctx, lambda: _lib.FastqStream(path1, path2, want_qual=bool(min_qual), pinned=True, target_seq_bytes=self.batch_seq_bytes))
+            names = np.array(names, dtype=object)
             abd32, tnf32 = feats.raw()
             abundance, tnf = abd32.astype(np.int64), tnf32.astype(np.int64)
             if reference_text_rounding:
                 abundance, tnf = _reference_text_rounding(abundance), _reference_text_rounding(tnf)
             self.timing = {n: ctx.timing(w)[0] for n, w in (("pack", 0), ("count", 1), ("group", 2), ("featurize", 3), ("normalize", 4))}
             self.features, self._ctx = feats, ctx
-            fq.close()
             if write_cache:  # same pickles the reference leaves: DataFrame, column 0 = label
                 for path, m in ((self._abd_pkl(), abundance), (self._tnf_pkl(), tnf)):
                     df = pd.DataFrame(m)

@@ -1,0 +1,146 @@
+"""Streaming featurization: a FASTQ of any size through the GPU in batches.
+
+The reference streams its input one cloud at a time (count_kmer.cpp:236-282) and never holds more than a
+few clouds in memory.  Here the unit is a batch (csrc/fastq.cpp: pg_fastq_stream_*), and because the
+abundance histogram needs the GLOBAL k-mer counts, the flow is two passes:
+
+    pass 1  for every batch: parse (host threads) -> pinned buffers -> H2D -> 2-bit pack -> count into the table.
+            The next batch is parsed while the GPU works on the current one.  The packed batch (0.5 B per base)
+            stays in HBM when it fits (pg_batch_compact); otherwise the file is parsed again in pass 2.
+    pass 2  for every batch: cloud grouping, TNF, abundance look-ups -> rows.  Rows of consecutive batches are the
+            reference's row order.
+
+With one batch this is exactly pg_extract_features (shared partition, one upload).
+"""
+from __future__ import annotations
+
+import queue
+import threading
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_BATCH_SEQ_BYTES = 6 << 30
+
+
+class _Prefetch:
+    """iterate a FastqStream one batch ahead on a feeder thread (pg_fastq_stream_next releases the GIL)"""
+
+    def __init__(self, stream, depth=1):
+        self.q = queue.Queue(maxsize=depth)
+        self.t = threading.Thread(target=self._run, args=(stream,), daemon=True)
+        self.t.start()
+
+    def _run(self, stream):
+        try:
+            while True:
+                fq = stream.next()
+                self.q.put(fq)
+                if fq is None:
+                    return
+        except BaseException as e:  # handed to the consumer
+            self.q.put(e)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+
+def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=True, reduce_table=None, resident_fraction=0.45):
+    """Whole path over a stream of batches.
+
+    open_stream: callable -> a fresh _lib.FastqStream (called again for pass 2 when the packed batches do not fit).
+    reduce_table: optional callable run between the passes (the multi-GPU all-reduce of the count tables).
+    Returns (names list[str], Features) - Features holds the rows of all batches on the device."""
+    if clear_table:
+        ctx.table_clear()
+    _, total = ctx.mem_info()
+    budget = int(total * resident_fraction)
+    stream = open_stream()
+    first = stream.next()
+    if first is None:  # empty input
+        stream.close()
+        empty = _lib.make_reads(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8))
+        b = ctx.upload_count(empty, keep_partition=False)
+        if reduce_table:
+            reduce_table()
+        f = ctx.featurize(b, np.zeros(1, np.uint8))
+        b.free()
+        return [], f
+    second = stream.next()
+    if second is None:
+        # one batch: keep the partition for the featurize pass (the fast path of pg_extract_features)
+        stream.close()
+        b = ctx.upload_count(first.reads, keep_partition=True)
+        if reduce_table:
+            reduce_table()
+        f = ctx.featurize(b, first.group_keep, first.n_groups)
+        labels = first.labels()
+        names = [labels[g] for g in f.row_groups().tolist()]
+        b.free()
+        first.close()
+        return names, f
+
+    # ---- pass 1: count every batch ----
+    held, resident, keep_resident = [], 0, True
+
+    def count_one(fq):
+        nonlocal resident, keep_resident
+        b = ctx.upload_count(fq.reads, keep_partition=False)
+        ctx.synchronize()  # the copies read fq's host buffers
+        packed = fq.reads.n_bytes // 2 + 9 * fq.reads.n_reads
+        if keep_resident and resident + packed > budget:
+            keep_resident = False
+            for hb in held:
+                hb[0].free()
+                hb[0] = None
+        if keep_resident:
+            b.compact()
+            resident += packed
+        else:
+            b.free()
+            b = None
+        keep = np.ctypeslib.as_array(_lib.C.cast(fq.group_keep, _lib.C.POINTER(_lib.C.c_uint8)), shape=(fq.n_groups,)).copy()
+        held.append([b, keep, fq.labels()])
+        fq.close()
+
+    count_one(first)
+    count_one(second)
+    for fq in _Prefetch(stream):
+        count_one(fq)
+    stream.close()
+    if reduce_table:
+        reduce_table()
+
+    # ---- pass 2: featurize every batch ----
+    names, parts = [], []
+    if keep_resident:
+        for b, keep, labels in held:
+            f = ctx.featurize(b, keep)
+            names += [labels[g] for g in f.row_groups().tolist()]
+            b.free()
+            parts.append(f)
+    else:
+        stream = open_stream()
+        for i, fq in enumerate(_Prefetch(stream)):
+            _, keep, labels = held[i]
+            if fq.n_groups != len(keep):
+                raise _lib.PgError(-5, "the input changed between the two passes")
+            b = ctx.upload(fq.reads)
+            f = ctx.featurize(b, keep)
+            ctx.synchronize()
+            names += [labels[g] for g in f.row_groups().tolist()]
+            b.free()
+            fq.close()
+            parts.append(f)
+        stream.close()
+    feats = ctx.concat_features(parts)
+    for f in parts:
+        f.free()
+    return names, feats

@@ -1,5 +1,6 @@
-"""2-GPU parity (NCCL): pangaea_b200.distributed.extract_features_sharded on two ranks ==
-the single-GPU result == the oracle.  Skipped on boxes with fewer than two GPUs."""
+"""Multi-rank parity: pangaea_b200.distributed on two or three ranks == the oracle over the whole file.
+Two flavours: NCCL on two GPUs (skipped on a one-GPU box) and - so that every box proves the multi-rank data path -
+the same code with the ranks sharing cuda:0 and gloo carrying the table all-reduce."""
 import os
 import socket
 
@@ -17,20 +18,28 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, path, out_dir):
+def _worker(rank, world, port, path, out_dir, backend, mode, k, batch_bytes):
     import torch
     import torch.distributed as dist
 
-    from pangaea_b200.distributed import extract_features_sharded, gather_rows
+    from pangaea_b200.distributed import extract_features_from_file, extract_features_sharded, gather_rows, gather_rows_named
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
-    fq = _lib.Fastq(path)
-    seq, off, flag, keep = fq.arrays()
-    ctx = _lib.Context(device=rank)
-    feats, shard = extract_features_sharded(ctx, seq, off, flag, keep)
-    merged = gather_rows(feats, shard, fq.label)
+    dev = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{dev}"))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _lib.Context(device=dev, k=k)
+    if mode == "arrays":  # every rank holds the parsed stream and slices its shard
+        fq = _lib.Fastq(path)
+        seq, off, flag, keep = fq.arrays()
+        feats, shard = extract_features_sharded(ctx, seq, off, flag, keep)
+        merged = gather_rows(feats, shard, fq.label)
+    else:                 # every rank parses only its byte range of the file
+        names, feats = extract_features_from_file(ctx, path, batch_seq_bytes=batch_bytes)
+        merged = gather_rows_named(names, feats)
     if rank == 0:
         names, abd, tnf = merged
         np.savez(os.path.join(out_dir, "merged.npz"), names=names, abd=abd, tnf=tnf, allow_pickle=True)
@@ -38,17 +47,30 @@ def _worker(rank, world, port, path, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one(tmp_path, oracle):
-    import torch
+def _run(tmp_path, oracle, world, backend, mode, k=15, batch_bytes=None, seed=17):
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    data = synth.generate(n_barcodes=300, mean_pairs=15, read_len=100, n_genomes=3, genome_len=80_000, frag_len=10_000, seed=17,
+    data = synth.generate(n_barcodes=300, mean_pairs=15, read_len=100, n_genomes=3, genome_len=80_000, frag_len=10_000, seed=seed,
                           unbarcoded_pairs=25, n_rate=0.002)
     path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
-    want_names, want_abd, want_tnf = oracle.featurize(path, None)
-    mp.spawn(_worker, args=(2, _free_port(), path, str(tmp_path)), nprocs=2, join=True)
+    want_names, want_abd, want_tnf = oracle.featurize(path, None, k=k)
+    mp.spawn(_worker, args=(world, _free_port(), path, str(tmp_path), backend, mode, k, batch_bytes), nprocs=world, join=True)
     got = np.load(tmp_path / "merged.npz", allow_pickle=True)
     assert list(got["names"]) == list(want_names)
     assert np.array_equal(got["abd"], want_abd) and np.array_equal(got["tnf"], want_tnf)
+
+
+@pytest.mark.parametrize("mode", ["arrays", "file"])
+def test_two_ranks_equal_one(tmp_path, oracle, mode):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(tmp_path, oracle, 2, "nccl", mode, batch_bytes=200_000 if mode == "file" else None)
+
+
+@pytest.mark.parametrize("world,mode,batch_bytes", [(2, "file", None), (3, "file", 150_000), (2, "arrays", None)])
+def test_ranks_sharing_one_gpu_equal_one(tmp_path, oracle, world, mode, batch_bytes):
+    """The multi-rank flow on ONE GPU: per-rank byte ranges (or shards), per-rank count tables, clamp, all-reduce (gloo),
+    per-rank featurize, rows gathered in rank order.  k = 13 keeps the all-reduced table at 128 MB."""
+    _run(tmp_path, oracle, world, "gloo", mode, k=13, batch_bytes=batch_bytes, seed=23)

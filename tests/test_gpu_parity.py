@@ -324,7 +324,7 @@ def test_counters_saturate_instead_of_wrapping(tmp_path, oracle, monkeypatch, en
     for i in range(60):  # 60 pairs in one barcode; every read = 40 G (26 poly-G windows) + 60 genome bases
         for _ in range(2):
             o = int(rng.integers(0, len(body) - 60))
-            reads.append("G" * 40 + body[o:o + 60])
+            reads.append("G" * 40 + "A" + body[o:o + 59])
     with open(tmp_path / "i.fq", "w") as f:
         for i in range(0, len(reads), 2):
             for r in reads[i:i + 2]:
@@ -631,3 +631,141 @@ def test_pipelined_upload_with_unpaired_reads_and_lower_case(tmp_path, oracle):
             assert np.array_equal(keys, wk) and np.array_equal(counts.astype(np.uint64), wv)
         finally:
             os.environ.pop("PG_SEG_WORDS", None)
+
+
+# ------------------------------------------------------------------------------------
+# streaming: files of any size in batches (pangaea_b200/stream.py)
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch_bytes,resident", [(60_000, 0.45), (250_000, 0.45), (60_000, 0.0), (10 ** 9, 0.45)])
+def test_streamed_batches_equal_one_batch_equal_oracle(tmp_path, oracle, batch_bytes, resident):
+    """count all batches, then featurize each (packed batches resident in HBM, or - resident = 0 - the file parsed twice):
+    rows == the oracle over the whole file."""
+    from pangaea_b200 import stream
+
+    data = synth.generate(n_barcodes=120, mean_pairs=18, read_len=100, n_genomes=3, genome_len=60_000, frag_len=9_000, seed=77,
+                          unbarcoded_pairs=40, n_rate=0.002)
+    path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    ctx = _ctx()
+    n_batches = len(list(_lib.FastqStream(path, target_seq_bytes=batch_bytes)))
+    assert n_batches > 3 if batch_bytes < 10 ** 6 else n_batches == 1
+    g_names, feats = stream.extract_features_streaming(
+        ctx, lambda: _lib.FastqStream(path, pinned=True, target_seq_bytes=batch_bytes), resident_fraction=resident)
+    g_abd, g_tnf = feats.raw()
+    assert g_names == list(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    a, t, w = feats.normalized()
+    oa, ot, ow = oracle.data_init(abd, tnf)
+    assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+
+
+def test_feature_streams_gzip_and_paired_input(tmp_path, oracle):
+    import gzip
+    import shutil
+
+    from conftest import GoldenCase
+    from pangaea_b200 import Feature
+
+    g = GoldenCase("synth_paired_minqual")
+    ft = Feature(_args(tmp_path / "p", reads1=g.reads1, reads2=g.reads2, min_length=g.params["min_length"]), "unused", batch_seq_bytes=3000)
+    names, abd, tnf = ft.extract_features(write_cache=False)
+    assert list(names) == list(g.abd_labels) and np.array_equal(abd, g.abd) and np.array_equal(tnf, g.tnf)
+    g = GoldenCase("synth_10x_l2000")
+    gz = tmp_path / "reads.fq.gz"
+    with open(g.path1, "rb") as a, gzip.open(gz, "wb") as b:
+        shutil.copyfileobj(a, b)
+    want = oracle.featurize(g.path1, None, mlen=g.params["min_length"])
+    ft = Feature(_args(tmp_path / "z", interleaved_reads=str(gz), min_length=g.params["min_length"]), "unused", batch_seq_bytes=20_000)
+    names, abd, tnf = ft.extract_features(write_cache=False)
+    assert list(names) == list(want[0]) and np.array_equal(abd, want[1]) and np.array_equal(tnf, want[2])
+    assert ft.features.rows == len(names)  # all batches' rows as one device-resident feature set
+
+
+def test_data_from_device_features_applies_the_csv_rounding(tmp_path, oracle):
+    """KAT-5 through the drop-in: a cloud with a tally >= 10^6 (bin 0 of a 7 000-pair cloud over a large genome).  The reference
+    normalises what pandas read from 6-significant-digit text (count_kmer.cpp:211); Data(features=Feature.features) must too."""
+    from pangaea_b200 import Data, Feature
+
+    data = synth.generate(n_barcodes=3, mean_pairs=7000, read_len=100, n_genomes=1, genome_len=6_000_000, frag_len=4_000_000, seed=9)
+    path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    assert abd.max() >= 1_000_000 and abd.max() % 10 != 0, "the case must exercise the rounding"
+    ft = Feature(_args(tmp_path, interleaved_reads=path), "unused")
+    g_names, g_abd, g_tnf = ft.extract_features(write_cache=False)
+    assert g_abd.dtype == np.float64 and np.array_equal(g_abd, oracle.text_round(abd)) and np.array_equal(g_tnf, oracle.text_round(tnf))
+    oa, ot, ow = oracle.data_init(oracle.text_round(abd), oracle.text_round(tnf))
+    for ds in (Data(g_names, g_abd, g_tnf), Data(g_names, g_abd, g_tnf, features=ft.features)):
+        assert np.array_equal(ds.abd, oa) and np.array_equal(ds.tnf, ot) and np.array_equal(ds.weights, ow)
+    exact = oracle.data_init(abd, tnf)[0]
+    assert not np.array_equal(exact, oa), "normalising the unrounded tallies gives different floats"
+
+
+# ------------------------------------------------------------------------------------
+# every BASELINE configuration, production geometry (no PG_* switches): a prefix against the oracle, the full size against
+# the direct path
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+def test_config_prefix_matches_oracle_with_default_geometry(tmp_path, oracle, name):
+    """The first 150 k pairs of each bench configuration (bench.py CONFIGS: read length, pairs per barcode, label length,
+    -l), generated on the device exactly as the bench generates them, written out as FASTQ and featurized by the oracle;
+    the GPU side runs with the default segment / slice / region geometry, through the host parser and the streaming driver."""
+    import bench
+    from pangaea_b200 import stream
+
+    cfg = bench.CONFIGS[name]
+    n = 150_000
+    for var in ("PG_SEG_WORDS", "PG_FEAT_SEG_WORDS", "PG_REGION_SLACK", "PG_FORCE_DIRECT", "PG_NO_SHARED", "PG_COUNT_L2", "PG_STASH_SEGMENTS"):
+        assert var not in os.environ
+    ctx = _ctx(min_length=cfg["min_length"])
+    s = synth.device_batch(ctx, n, cfg["read_len"], n_barcodes=max(1, n // cfg["pairs_per_barcode"]), n_genomes=cfg["n_genomes"], seed=cfg["seed"])
+    path = synth.write_batch_fastq(str(tmp_path / "prefix.fq"), s["seq"].cpu().numpy(), cfg["read_len"], s["bc_start"], n,
+                                   barcode_len=cfg["barcode_len"])
+    names, abd, tnf = oracle.featurize(path, None, mlen=cfg["min_length"])
+    # (a) device-resident batch, as the bench runs it
+    keep = np.ones(s["n_groups"], np.uint8)
+    keep[0] = 0
+    b = ctx.adopt(s["reads"], keepalive=s)
+    ctx.count(b)
+    f = ctx.featurize(b, keep)
+    g_abd, g_tnf = f.raw()
+    assert f.rows == len(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    f.free(); b.free()
+    # (b) the drop-in route: host parser -> streamed batches
+    g_names, f = stream.extract_features_streaming(ctx, lambda: _lib.FastqStream(path, pinned=True, target_seq_bytes=40_000_000))
+    g_abd, g_tnf = f.raw()
+    assert g_names == list(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    a, t, w = f.normalized()
+    oa, ot, ow = oracle.data_init(abd, tnf)
+    assert np.array_equal(a, oa) and np.array_equal(t, ot) and np.array_equal(w, ow)
+
+
+def test_full_size_sliced_path_equals_direct_path(monkeypatch):
+    """The headline workload at its FULL size (50 M pairs, 5 segments of 2^26 words, 64 slices at real fill, sub-regions at
+    real fill): the sliced production path against the direct path (count_kernel / featurize_kernel - no partitioning at
+    all, pinned to the oracle by the small tests above).  Tables and matrices must agree bit for bit."""
+    import torch
+
+    import bench
+
+    cfg = bench.CONFIGS["c2"]
+    n = cfg["pairs"]
+    results = {}
+    for direct in ("0", "1"):
+        monkeypatch.setenv("PG_FORCE_DIRECT", direct)
+        ctx = _ctx()
+        s = synth.device_batch(ctx, n, cfg["read_len"], n_barcodes=n // cfg["pairs_per_barcode"], n_genomes=cfg["n_genomes"], seed=cfg["seed"])
+        keep = np.ones(s["n_groups"], np.uint8)
+        keep[0] = 0
+        b = ctx.adopt(s["reads"], keepalive=s)
+        ctx.count(b)
+        f = ctx.featurize(b, keep)
+        ctx.synchronize()
+        sliced = ctx.timing(_lib.T_COUNT_SCATTER)[0] > 0
+        assert sliced == (direct == "0")
+        results[direct] = (ctx.table_as_torch().clone(), f.torch(_lib.ABD_RAW).clone(), f.torch(_lib.TNF_RAW).clone())
+        f.free(); b.free(); del s
+        ctx.close()
+        torch.cuda.empty_cache()
+    (t0, a0, n0), (t1, a1, n1) = results["0"], results["1"]
+    assert a0.shape[0] > 400_000
+    assert torch.equal(t0, t1), "k-mer tables differ"
+    assert torch.equal(a0, a1) and torch.equal(n0, n1), "feature matrices differ"

@@ -130,12 +130,11 @@ def test_parallel_reader_equals_sequential_reader(tmp_path, monkeypatch, threads
     (tmp_path / "one.fq").write_bytes(b"@a BX:Z:AA-1\nACGT\n+\nIIII\n@a BX:Z:AA-1\nGG\n+\n>>")
     files.append(str(tmp_path / "one.fq"))
     for path in files:
-        monkeypatch.setenv("PG_FASTQ_THREADS", "1")
+        monkeypatch.setenv("PG_FASTQ_SEQUENTIAL", "1")   # the getline-style reader (also used for gzip / paired input)
         want = _parse_all(path, want_qual=True)
+        monkeypatch.delenv("PG_FASTQ_SEQUENTIAL")
         monkeypatch.setenv("PG_FASTQ_THREADS", threads)
-        monkeypatch.setenv("PG_FASTQ_PARALLEL_MIN", "0")
         got = _parse_all(path, want_qual=True)
-        monkeypatch.delenv("PG_FASTQ_PARALLEL_MIN")
         for a, b in zip(want[:4], got[:4]):
             assert np.array_equal(a, b), path
         assert want[4] == got[4] and want[5] == got[5], path
@@ -181,14 +180,217 @@ def test_parallel_reader_property_random_text(tmp_path, monkeypatch):
         path = str(tmp_path / f"h{counter[0] % 4}.fq")
         data = b"\n".join(lines) + (b"\n" if final_newline and lines else b"")
         open(path, "wb").write(data)
-        monkeypatch.setenv("PG_FASTQ_THREADS", "1")
+        monkeypatch.setenv("PG_FASTQ_SEQUENTIAL", "1")   # the getline-style reader (also used for gzip / paired input)
         want = _parse_all(path, want_qual=True)
+        monkeypatch.delenv("PG_FASTQ_SEQUENTIAL")
         monkeypatch.setenv("PG_FASTQ_THREADS", threads)
-        monkeypatch.setenv("PG_FASTQ_PARALLEL_MIN", "0")
         got = _parse_all(path, want_qual=True)
-        monkeypatch.delenv("PG_FASTQ_PARALLEL_MIN")
         for a, b in zip(want[:4], got[:4]):
             assert np.array_equal(a, b), data
         assert want[4] == got[4] and want[5] == got[5], data
 
     check()
+
+
+# ------------------------------------------------------------------------------------
+# the reader as a stream of batches, and byte ranges for ranks
+# ------------------------------------------------------------------------------------
+def _chunk_tuple(fq, want_qual):
+    seq, off, flag, keep = (a.copy() for a in fq.arrays())
+    r = fq.reads
+    qual = bytes(np.ctypeslib.as_array(C.cast(r.qual, C.POINTER(C.c_uint8)), shape=(r.n_bytes,))) if want_qual and r.n_bytes else b""
+    labels = [fq.label(g) for g in range(fq.n_groups)]
+    return seq, off, flag, keep, labels, qual
+
+
+def _stream_all(path, target, want_qual=True, path2=None, **kw):
+    s = _lib.FastqStream(path, path2, want_qual=want_qual, target_seq_bytes=target, **kw)
+    chunks = []
+    for fq in s:
+        chunks.append(_chunk_tuple(fq, want_qual))
+        fq.close()
+    s.close()
+    return chunks
+
+
+def _concat(chunks):
+    """what the batches of a stream add up to, in the layout of one batch"""
+    if not chunks:
+        return np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8), [""], b""
+    seq = np.concatenate([c[0] for c in chunks])
+    base, offs = 0, [np.zeros(1, np.int64)]
+    for c in chunks:
+        offs.append(c[1][1:] + base)
+        base += int(c[1][-1])
+    flag = np.concatenate([c[2] for c in chunks])
+    labels = list(chunks[0][4])
+    for prev, c in zip(chunks, chunks[1:]):
+        assert c[4][0] == prev[4][-1], "label 0 of a batch = label of the cloud that was open when the previous one ended"
+        labels += c[4][1:]
+    return seq, np.concatenate(offs), flag, labels, b"".join(c[5] for c in chunks)
+
+
+def _check_cut_points(chunks):
+    for c in chunks[:-1]:
+        seq, off, flag, keep, labels, _ = c
+        assert len(flag), "no empty batch in the middle of a stream"
+        assert (flag[-1] & 1) or labels[-1] == "", "a batch ends at a cloud flush or inside a cloud that is dropped whole"
+        assert len(keep) == len(labels) == 1 + int((flag & 1).sum())
+        assert [bool(k) for k in keep] == [l != "" for l in labels]
+
+
+def _stream_files(tmp_path):
+    from pangaea_b200 import synth
+
+    files = [os.path.join(ROOT, "tests", "golden", d, "reads.fq") for d in ("kat1_interleaved_10x", "edge_ragged", "synth_10x_l2000")]
+    data = synth.generate(n_barcodes=60, mean_pairs=3, read_len=37, n_genomes=2, genome_len=5000, frag_len=1000, seed=5, unbarcoded_pairs=25)
+    files.append(synth.write_interleaved(str(tmp_path / "stlfr.fq"), data, style="stlfr"))
+    files.append(synth.write_interleaved(str(tmp_path / "tenx.fq"), data))
+    (tmp_path / "trunc.fq").write_bytes(open(files[-1], "rb").read()[:-37])
+    files.append(str(tmp_path / "trunc.fq"))
+    # single-pair barcodes back to back (every pair flushes), then a long one
+    recs = b"".join(b"@r%d BX:Z:%s-1\nACGTACGTAC\n+\nIIIIIIIIII\n" % (i // 2, b"ACGT"[(i // 2) % 4:(i // 2) % 4 + 1] * 3) for i in range(40))
+    recs += b"".join(b"@q%d BX:Z:TTT-1\nGGGTACGTAC\n+\nIIIIIIIIII\n" % (i // 2) for i in range(60))
+    (tmp_path / "singles.fq").write_bytes(recs)
+    files.append(str(tmp_path / "singles.fq"))
+    return files
+
+
+@pytest.mark.parametrize("sequential", [False, True])
+def test_stream_batches_add_up_to_the_whole_file(tmp_path, monkeypatch, sequential):
+    if sequential:
+        monkeypatch.setenv("PG_FASTQ_SEQUENTIAL", "1")
+    monkeypatch.setenv("PG_FASTQ_THREADS", "3")
+    for path in _stream_files(tmp_path):
+        whole = _parse_all(path, want_qual=True)
+        for target in (1, 150, 1000, 20_000, 10 ** 9):
+            chunks = _stream_all(path, target)
+            _check_cut_points(chunks)
+            seq, off, flag, labels, qual = _concat(chunks)
+            assert np.array_equal(seq, whole[0]) and np.array_equal(off, whole[1]) and np.array_equal(flag, whole[2]), (path, target)
+            assert labels == whole[4] and qual == whole[5], (path, target)
+            if target <= 150 and len(whole[2]) > 20:
+                assert len(chunks) > 2
+
+
+def test_stream_of_paired_and_gzip_input(tmp_path):
+    import gzip
+    import shutil
+
+    g = os.path.join(ROOT, "tests", "golden", "synth_paired_minqual")
+    whole = _lib.Fastq(os.path.join(g, "r1.fq"), os.path.join(g, "r2.fq"), want_qual=True)
+    wt = _chunk_tuple(whole, True)
+    for target in (300, 5000):
+        chunks = _stream_all(os.path.join(g, "r1.fq"), target, path2=os.path.join(g, "r2.fq"))
+        assert len(chunks) > 1
+        _check_cut_points(chunks)
+        seq, off, flag, labels, qual = _concat(chunks)
+        assert np.array_equal(seq, wt[0]) and np.array_equal(off, wt[1]) and np.array_equal(flag, wt[2]) and labels == wt[4] and qual == wt[5]
+    src = os.path.join(ROOT, "tests", "golden", "synth_10x_l2000", "reads.fq")
+    gz = tmp_path / "reads.fq.gz"
+    with open(src, "rb") as a, gzip.open(gz, "wb") as b:
+        shutil.copyfileobj(a, b)
+    wt = _parse_all(src, want_qual=True)
+    chunks = _stream_all(str(gz), 4000)
+    assert len(chunks) > 2
+    seq, off, flag, labels, qual = _concat(chunks)
+    assert np.array_equal(seq, wt[0]) and np.array_equal(flag, wt[2]) and labels == wt[4] and qual == wt[5]
+    # a truncated gzip stream is an error, not a shorter file
+    raw = gz.read_bytes()
+    (tmp_path / "cut.fq.gz").write_bytes(raw[: len(raw) * 2 // 3])
+    with pytest.raises(_lib.PgError):
+        _lib.Fastq(str(tmp_path / "cut.fq.gz"))
+    with pytest.raises(_lib.PgError):  # byte ranges need plain text
+        _lib.FastqStream(str(gz), byte_lo=10, byte_hi=100, lines_before_lo=0)
+
+
+def _ranges(path, world):
+    size = os.path.getsize(path)
+    cuts = [size * r // world for r in range(world)] + [size]
+    lines = [_lib.count_lines(path, cuts[r], cuts[r + 1]) for r in range(world)]
+    before = [sum(lines[:r]) for r in range(world)]
+    return [(cuts[r], cuts[r + 1] if r + 1 < world else -1, before[r]) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_rank_byte_ranges_partition_the_file(tmp_path, monkeypatch, world):
+    """Every rank opens its own byte range (pg_fastq_stream_open byte_lo / byte_hi); exchanged: newline counts only.  The
+    ranks' batches, in rank order, add up to the whole file - and each rank starts at a cloud flush, so its clouds are whole."""
+    monkeypatch.setenv("PG_FASTQ_THREADS", "2")
+    for path in _stream_files(tmp_path):
+        whole = _parse_all(path, want_qual=True)
+        for target in (0, 700):
+            chunks = []
+            for lo, hi, before in _ranges(path, world):
+                mine = _stream_all(path, target, byte_lo=lo, byte_hi=hi, lines_before_lo=before)
+                chunks += mine
+            _check_cut_points(chunks)
+            seq, off, flag, labels, qual = _concat(chunks)
+            assert np.array_equal(seq, whole[0]) and np.array_equal(off, whole[1]) and np.array_equal(flag, whole[2]), (path, world, target)
+            assert labels == whole[4] and qual == whole[5], (path, world, target)
+
+
+def test_stream_property_random_text(tmp_path, monkeypatch):
+    """hypothesis: hostile text, random batch sizes and rank counts - batches and ranges always add up to the one-batch parse."""
+    from hypothesis import given, settings, strategies as st
+
+    header = st.one_of(
+        st.builds(lambda n, bc: b"@r%d BX:Z:%s-1" % (n, bc), st.integers(0, 99), st.sampled_from([b"AAAA", b"AAAC", b"CC", b"", b"GG-TT"])),
+        st.builds(lambda n, bc, m: b"@r%d#%s/%d" % (n, bc, m), st.integers(0, 99), st.sampled_from([b"1_1_1", b"0_0_0", b"2_2_2", b""]), st.integers(1, 2)),
+        st.sampled_from([b"@plain", b"", b"@x\tBX:Z:AAAA", b"@y BX:Z:", b"# /", b"@z\r"]))
+    seq = st.one_of(st.text(alphabet="ACGTNacgt", min_size=0, max_size=40).map(str.encode), st.sampled_from([b"", b"ACGT\r", b"@ACGT", b"+"]))
+    line = st.one_of(header, seq, st.sampled_from([b"+", b"IIII", b"", b"????"]))
+    record = st.tuples(header, seq, st.just(b"+"), seq).map(lambda t: list(t))
+    text = st.one_of(st.lists(record, max_size=40).map(lambda rs: [l for r in rs for l in r]), st.lists(line, max_size=80))
+    counter = [0]
+
+    @settings(max_examples=300, deadline=None)
+    @given(lines=text, final_newline=st.booleans(), threads=st.sampled_from(["1", "2", "3"]), target=st.sampled_from([1, 30, 200, 0]),
+           world=st.integers(1, 4), sequential=st.booleans())
+    def check(lines, final_newline, threads, target, world, sequential):
+        counter[0] += 1
+        path = str(tmp_path / f"s{counter[0] % 4}.fq")
+        data = b"\n".join(lines) + (b"\n" if final_newline and lines else b"")
+        open(path, "wb").write(data)
+        monkeypatch.setenv("PG_FASTQ_THREADS", threads)
+        whole = _parse_all(path, want_qual=True)
+        if sequential:
+            monkeypatch.setenv("PG_FASTQ_SEQUENTIAL", "1")
+            chunks = _stream_all(path, target)
+            monkeypatch.delenv("PG_FASTQ_SEQUENTIAL")
+        else:
+            chunks = []
+            for lo, hi, before in _ranges(path, world):
+                chunks += _stream_all(path, target, byte_lo=lo, byte_hi=hi, lines_before_lo=before)
+        _check_cut_points(chunks)
+        seq_, off, flag, labels, qual = _concat(chunks)
+        assert np.array_equal(seq_, whole[0]) and np.array_equal(off, whole[1]) and np.array_equal(flag, whole[2]), data
+        assert labels == whole[4] and qual == whole[5], data
+
+    check()
+
+
+@pytest.mark.parametrize("target", [400, 3000])
+def test_streamed_batches_give_the_reference_rows(tmp_path, oracle, golden, target):
+    """Contract-level check of the streaming flow: count over all batches, featurize batch by batch, concatenate the rows
+    == the reference tools' outputs for the whole file (golden vectors)."""
+    if golden.reads2 and not golden.interleaved:
+        path1, path2 = golden.reads1, golden.reads2
+    else:
+        path1, path2 = golden.path1, None
+    p = golden.params
+    table = oracle.Table()
+    table.load_dump(golden.dump, p["k"])
+    names, abd, tnf = [], [], []
+    n_chunks = 0
+    s = _lib.FastqStream(path1, path2, target_seq_bytes=target)
+    for fq in s:
+        n_chunks += 1
+        seq, off, flag, keep = fq.arrays()
+        labels = [fq.label(g) for g in range(fq.n_groups)]
+        n, a, t = contract_features(seq, off, flag, keep, labels, table, p["k"], p["tnf_k"], p["min_length"], p["vector_size"], p["window_size"])
+        names += n; abd.append(a); tnf.append(t)
+        fq.close()
+    assert names == list(golden.abd_labels) == list(golden.tnf_labels)
+    if names:
+        assert np.array_equal(np.concatenate(abd), golden.abd) and np.array_equal(np.concatenate(tnf), golden.tnf)
