@@ -218,12 +218,28 @@ __device__ __noinline__ void feat_word_direct(const FeatParams& P, int64_t j, ui
 // ---------------------------------------------------------------------------
 template <bool FEAT>
 struct ScatterSmem {
-    uint32_t cnt[kMaxBuckets + 1];         // windows of this tile per slice (+1: dummy slot of non-emitting windows)
-    uint32_t n_run[kMaxBuckets];           // entries to copy out per slice (0 when the staging row overflowed)
-    unsigned long long gbase[kMaxBuckets]; // where this tile's run starts in the entry buffer
-    unsigned long long ovf;                // bit b: the staging row of slice b overflowed in this tile
+    uint32_t cnt[2][kMaxBuckets + 8];      // windows of the tile per slice (+ dummy slot of non-emitting windows); double-buffered:
+                                           // the counters of tile t are still read (overflow check) while those of t + 1 are zeroed
     alignas(16) uint32_t stage[(kMaxBuckets + 1) * ScatterCfg<FEAT>::kStageStride];
 };
+
+// ---- bulk copies (TMA engine, no tensor map): shared -> global, completion tracked per thread in bulk groups ----
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long bulk_policy_evict_first()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// bytes: multiple of 16; both addresses 16 B aligned
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct ScatterParams {
     const uint64_t* codes;
@@ -266,11 +282,19 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
     ScatterSmem<FEAT>& S = *reinterpret_cast<ScatterSmem<FEAT>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = KT ? KT : Q.k;
-    uint32_t *const cnt = S.cnt, *const stage = S.stage;
+    uint32_t* const stage = S.stage;
     const int64_t n_tiles = (Q.w1 - Q.w0 + Cfg::kTileWords - 1) / Cfg::kTileWords;
+    const unsigned long long policy = bulk_policy_evict_first(); // the entries are streamed: written once, read once much later
+    if (threadIdx.x <= kMaxBuckets) { S.cnt[0][threadIdx.x] = 0u; S.cnt[1][threadIdx.x] = 0u; }
+    int cur = 0;
 
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (threadIdx.x <= kMaxBuckets) cnt[threadIdx.x] = 0u;
+    // Per tile: bin into the staging rows -> barrier -> the 64 lanes of warps 0 and 1 each claim the run of one slice and
+    // hand the row to the copy engine (cp.async.bulk shared -> global) -> every warp moves on to the loads of its next
+    // tile; the rows are reused once the engine has read them (wait_group.read + the barrier at the top).  Nobody copies
+    // with LDS / STG, and there are two barriers per tile instead of four.
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, cur ^= 1) {
+        uint32_t* const cnt = S.cnt[cur];
+        if (warp < 2) bulk_wait_read(); // the engine is done reading the rows of the previous tile
         __syncthreads();
 
         const int64_t tile0 = Q.w0 + t * Cfg::kTileWords;
@@ -375,85 +399,61 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 }
             });
         }
+        bulk_store_fence(); // the rows were written through the generic proxy; the copy engine reads them through the async proxy
         __syncthreads();
+        if (threadIdx.x <= kMaxBuckets) S.cnt[cur ^ 1][threadIdx.x] = 0u; // (last read before the barrier at the top of this trip)
 
-        // ---- claim one run per slice in the entry buffer ----
-        if (warp == 0) { // n_buckets <= 64: lane owns slices `lane` and `lane + 32`
-            unsigned long long ovf = 0ull;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int b = lane + 32 * h;
+        // ---- claim one run per slice in the entry buffer and hand it to the copy engine: lane <-> slice ----
+        if (warp < 2) {
+            const int b = 32 * warp + lane;
+            if (b < Q.geo.n_buckets) {
                 const uint32_t c = cnt[b];
-                const bool over = c > (uint32_t)CAP;
-                const uint32_t n = over ? 0u : c;
-                const uint32_t claim = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
-                unsigned long long gb = kOverflowRun;
-                if (claim) {
-                    const unsigned long long off = atomicAdd(&Q.st->cursors[b], (unsigned long long)claim);
-                    if (off + claim > Q.geo.cap) atomicMin(&Q.st->limits[b], off);
-                    else gb = (unsigned long long)b * Q.geo.cap + off;
-                }
-                S.n_run[b] = n;
-                S.gbase[b] = gb;
-                ovf |= (unsigned long long)__ballot_sync(0xffffffffu, over) << (32 * h);
-            }
-            if (lane == 0) S.ovf = ovf;
-        }
-        __syncthreads();
-
-        // ---- copy the runs out: one warp per slice, coalesced ----
-        for (int b = warp; b < Q.geo.n_buckets; b += Cfg::kThreads / 32) {
-            const uint32_t n = S.n_run[b];
-            if (!n) continue;
-            const uint32_t* src = stage + b * STRIDE;
-            const unsigned long long gb = S.gbase[b];
-            if (gb != kOverflowRun) {
+                const uint32_t n = c > (uint32_t)CAP ? 0u : c; // a row that overflowed is redone below
                 const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
-                PG_CHECK(n <= (uint32_t)CAP && gb >= (unsigned long long)b * Q.geo.cap && gb + n_pad <= (unsigned long long)(b + 1) * Q.geo.cap && (gb & 3ull) == 0ull);
-                uint4* dst = reinterpret_cast<uint4*>(Q.entries + gb);
-                uint32_t e = 4u * lane;
-                for (; e + 4u <= n; e += 128u) __stcs(dst + (e >> 2), *reinterpret_cast<const uint4*>(src + e)); // whole quads
-                if (e < n_pad) { // the quad that holds the end of the run, and the padding after it
-                    uint4 v = *reinterpret_cast<const uint4*>(src + e);
-                    if (e + 0u >= n) v.x = kInvalidEntry;
-                    if (e + 1u >= n) v.y = kInvalidEntry;
-                    if (e + 2u >= n) v.z = kInvalidEntry;
-                    if (e + 3u >= n) v.w = kInvalidEntry;
-                    __stcs(dst + (e >> 2), v);
-                }
-                if (FEAT && (uint32_t)lane < (n_pad >> 5)) Q.meta[(gb >> 5) + lane] = tile_base;
-            } else if (MODE == kScatterFeat) { // region full: look the run up here (whole warp stays in the loop for the reduction)
-                for (uint32_t e0 = 0; e0 < n; e0 += 32) {
-                    const uint32_t e = e0 + lane;
-                    unsigned long long key = 0;
-                    bool live = false;
-                    if (e < n) {
-                        const uint32_t v = src[e];
-                        const uint32_t r = (uint32_t)tile_base + delta_of_entry(v);
-                        live = abd_key(P, __ldg(P.table.counts + (((uint32_t)b << kSliceBits) | ((v >> 3) & Q.geo.low_mask))), r, key);
+                if (n) {
+                    uint32_t* row = stage + b * STRIDE;
+                    const unsigned long long off = atomicAdd(&Q.st->cursors[b], (unsigned long long)n_pad);
+                    if (off + n_pad <= Q.geo.cap) {
+                        const unsigned long long gb = (unsigned long long)b * Q.geo.cap + off;
+                        PG_CHECK(n <= (uint32_t)CAP && (gb & 3ull) == 0ull && gb + n_pad <= (unsigned long long)(b + 1) * Q.geo.cap);
+                        for (uint32_t e = n; e < n_pad; ++e) row[e] = kInvalidEntry; // (CAP is a multiple of the padding: it fits)
+                        bulk_store_fence();
+                        bulk_store(Q.entries + gb, row, n_pad * 4u, policy);
+                        if (FEAT) for (uint32_t i = 0; i < (n_pad >> 5); ++i) Q.meta[(gb >> 5) + i] = tile_base;
+                    } else { // region full (pathological repeats): this lane applies / looks up the run itself
+                        atomicMin(&Q.st->limits[b], off);
+                        for (uint32_t e = 0; e < n; ++e) {
+                            const uint32_t v = row[e];
+                            const uint32_t idx = ((uint32_t)b << kSliceBits) | ((v >> 3) & Q.geo.low_mask);
+                            if (MODE == kScatterFeat) {
+                                unsigned long long key;
+                                if (abd_key(P, __ldg(P.table.counts + idx), (uint32_t)tile_base + delta_of_entry(v), key))
+                                    atomicAdd(P.abd + (int64_t)(key >> 32) * P.vs + (uint32_t)key, 1u);
+                            } else {
+                                table_add_checked(Q.table + idx, 1u, Q.sat);
+                            }
+                        }
+                        if (MODE == kScatterShared) *Q.lost = 1u;
                     }
-                    abd_reduce_warp(P, live, key);
                 }
-            } else { // region full: apply the run here
-                for (uint32_t e = lane; e < n; e += 32) table_add_checked(Q.table + (((uint32_t)b << kSliceBits) | ((src[e] >> 3) & Q.geo.low_mask)), 1u, Q.sat);
-                if (MODE == kScatterShared && lane == 0) *Q.lost = 1u;
             }
+            bulk_commit();
         }
 
-        // ---- staging rows that overflowed: walk the tile again, those slices go straight to the table ----
-        const unsigned long long ovf = S.ovf;
-        if (ovf != 0ull && (v0 | v1 | v2) != 0u) {
+        // ---- staging rows that overflowed (tandem repeats, poly-G): walk the tile again, those slices go straight to the table ----
+        const bool any_ovf = __any_sync(0xffffffffu, cnt[lane] > (uint32_t)CAP || cnt[lane + 32] > (uint32_t)CAP);
+        if (any_ovf && (v0 | v1 | v2) != 0u) {
             for (int i = 0; i < 32; ++i) {
                 if (!(((v0 | v1 | v2) >> i) & 1u)) continue;
                 const uint32_t y = window_y(lo, hi, i, k);
-                if (!((ovf >> (y >> 26)) & 1ull)) continue;
+                if (cnt[y >> 26] <= (uint32_t)CAP) continue;
                 if (MODE == kScatterFeat) abd_direct(P, y, ((v0 >> i) & 1u) ? row0 : row1);
                 else table_add_checked(Q.table + (y >> 3), 1u, Q.sat);
             }
             if (MODE == kScatterShared) *Q.lost = 1u;
         }
-        __syncthreads();
     }
+    if (warp < 2) bulk_wait_all(); // the rows must outlive the copies
 }
 
 // entries per region after a scatter launch (the cursors are reset for the next segment)

@@ -55,10 +55,7 @@ __global__ void sub_reset_kernel(SubState s, SubGeom geo)
 }
 
 struct SplitSmem {
-    uint32_t cnt[kSubFan + 1];            // +1: dummy row of the padding lanes
-    uint32_t n_run[kSubFan];
-    uint32_t off[kSubFan];                // offset of the run inside its sub-region, kSubOverflow when the region is full
-    uint32_t ovf[kSubFan / 32];           // staging rows that overflowed in this tile
+    uint32_t cnt[2][kSubFan + 8];         // +1: dummy row of the padding lanes; double-buffered like ScatterSmem::cnt
     unsigned long long fill[kMaxBuckets];
     unsigned long long tile_base[kMaxBuckets + 1];
     alignas(16) uint16_t stage[(kSubFan + 1) * kSplitStride];
@@ -70,7 +67,7 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SplitSmem& S = *reinterpret_cast<SplitSmem*>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
         for (int b = 0; b < geo.n_buckets; ++b) {
@@ -81,16 +78,17 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
         }
         S.tile_base[geo.n_buckets] = acc;
     }
+    for (int i = threadIdx.x; i <= kSubFan; i += kSplitThreads) { S.cnt[0][i] = 0u; S.cnt[1][i] = 0u; }
     __syncthreads();
     const unsigned long long n_tiles = S.tile_base[geo.n_buckets];
-    uint32_t* const cnt = S.cnt;
+    const unsigned long long policy = bulk_policy_evict_first();
     uint16_t* const stage = S.stage;
-    int b = 0;
-    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int b = 0, cur = 0;
+    // Same shape as the scatter kernel (bucket.cuh): bin -> barrier -> thread s claims the run of sub-slice s and hands its
+    // row to the copy engine (cp.async.bulk) -> on to the next tile; rows are reused after wait_group.read + the top barrier.
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x, cur ^= 1) {
         while (S.tile_base[b + 1] <= t) ++b; // tiles only grow
-        for (int i = threadIdx.x; i <= kSubFan; i += kSplitThreads) cnt[i] = 0u;
-        if (threadIdx.x < kSubFan / 32) S.ovf[threadIdx.x] = 0u;
-        __syncthreads();
+        uint32_t* const cnt = S.cnt[cur];
         const unsigned long long off = (t - S.tile_base[b]) * kSplitTile;
         const uint32_t n = (uint32_t)min((unsigned long long)kSplitTile, S.fill[b] - off);
         const uint4* src = reinterpret_cast<const uint4*>(entries + (unsigned long long)b * geo.cap + off);
@@ -100,6 +98,8 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
             const uint32_t i4 = u * kSplitThreads + threadIdx.x; // coalesced 16 B per lane
             e[u] = (4u * i4 < n) ? __ldcs(src + i4) : make_uint4(0, 0, 0, 0);
         }
+        if (threadIdx.x < kSubFan) bulk_wait_read(); // the engine is done reading the rows of the previous tile
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < kSplitPer / 4; ++u) {
             const uint32_t i0 = 4u * (u * kSplitThreads + threadIdx.x);
@@ -112,53 +112,45 @@ bucket_split_kernel(const uint32_t* __restrict__ entries, BucketGeom geo, const 
 #pragma unroll
             for (int c = 0; c < 4; ++c) stage[sub[c] * kSplitStride + min(slot[c], (uint32_t)(kSplitCap - 1))] = (uint16_t)((v[c] >> 3) & (kSubWords - 1));
         }
+        bulk_store_fence();
         __syncthreads();
-        if (threadIdx.x < kSubFan) { // claim one run per sub-region
+        for (int i = threadIdx.x; i <= kSubFan; i += kSplitThreads) S.cnt[cur ^ 1][i] = 0u;
+        if (threadIdx.x < kSubFan) { // claim one run per sub-region and hand it to the copy engine
             const int s = threadIdx.x;
             const uint32_t c = cnt[s];
-            const bool over = c > (uint32_t)kSplitCap;
-            const uint32_t m = over ? 0u : c;
-            uint32_t o = kSubOverflow;
+            const uint32_t m = c > (uint32_t)kSplitCap ? 0u : c; // a row that overflowed is redone below
             if (m) {
                 const int idx = b * kSubFan + s;
                 const uint32_t claim = (m + 7u) & ~7u;
+                uint16_t* row = stage + s * kSplitStride;
                 const uint32_t at = atomicAdd(ss.cursors + idx, claim); // (wraps only beyond 2^32 entries in one sub-slice of one segment)
-                if ((unsigned long long)at + claim > sg.cap) atomicMin(ss.limits + idx, min(at, sg.cap));
-                else o = at;
+                if ((unsigned long long)at + claim <= sg.cap) {
+                    PG_CHECK(m <= (uint32_t)kSplitCap && (at & 7u) == 0u);
+                    for (uint32_t i = m; i < claim; ++i) row[i] = kSubInvalid; // pad the run to whole 16 B quads
+                    bulk_store_fence();
+                    bulk_store(entries2 + (unsigned long long)idx * sg.cap + at, row, claim * 2u, policy);
+                } else { // sub-region full: apply the run here
+                    atomicMin(ss.limits + idx, min(at, sg.cap));
+                    uint32_t* sub_table = table + ((size_t)b << kSliceBits) + ((size_t)s << kSubBits);
+                    for (uint32_t i = 0; i < m; ++i) table_add_checked(sub_table + row[i], 1u, sat);
+                }
             }
-            S.n_run[s] = m;
-            S.off[s] = o;
-            for (uint32_t i = m; i < ((m + 7u) & ~7u); ++i) stage[s * kSplitStride + i] = kSubInvalid; // pad the run to whole 16 B quads here,
-                                                                                                      // so the copy below is a plain loop
-            if (over) atomicOr(&S.ovf[s >> 5], 1u << (s & 31));
+            bulk_commit();
         }
-        __syncthreads();
-        // copy the runs out: 8 lanes per sub-slice, 8 entries (16 B) per lane per trip
-        for (int s = 4 * warp + (lane >> 3); s < kSubFan; s += kSplitThreads / 8) {
-            const uint32_t m = S.n_run[s];
-            if (!m) continue;
-            const uint16_t* row = stage + s * kSplitStride;
-            const uint32_t o = S.off[s];
-            if (o != kSubOverflow) {
-                PG_CHECK(m <= (uint32_t)kSplitCap && (o & 7u) == 0u && (unsigned long long)o + ((m + 7u) & ~7u) <= sg.cap);
-                uint4* dst = reinterpret_cast<uint4*>(entries2 + (unsigned long long)(b * kSubFan + s) * sg.cap + o);
-                for (uint32_t i = 8u * (lane & 7); i < m; i += 64u) __stcs(dst + (i >> 3), *reinterpret_cast<const uint4*>(row + i));
-            } else { // sub-region full: apply the run here
-                uint32_t* sub_table = table + ((size_t)b << kSliceBits) + ((size_t)s << kSubBits);
-                for (uint32_t i = lane & 7; i < m; i += 8) table_add_checked(sub_table + row[i], 1u, sat);
-            }
-        }
-        // staging rows that overflowed: those sub-slices' entries of this tile go straight to the table
-        if (S.ovf[0] | S.ovf[1] | S.ovf[2] | S.ovf[3] | S.ovf[4] | S.ovf[5] | S.ovf[6] | S.ovf[7]) {
-            for (uint32_t i = threadIdx.x; i < n; i += kSplitThreads) { // rare: re-read the tile
+        // staging rows that overflowed: those sub-slices' entries of this tile go straight to the table (rare: re-read the tile)
+        bool any_ovf = false;
+#pragma unroll
+        for (int j = 0; j < kSubFan / 32; ++j) any_ovf |= cnt[lane + 32 * j] > (uint32_t)kSplitCap;
+        if (__any_sync(0xffffffffu, any_ovf)) {
+            for (uint32_t i = threadIdx.x; i < n; i += kSplitThreads) {
                 const uint32_t v = __ldg(entries + (unsigned long long)b * geo.cap + off + i);
                 if (v == kInvalidEntry) continue;
                 const uint32_t sub = (v >> (3 + kSubBits)) & (kSubFan - 1);
-                if ((S.ovf[sub >> 5] >> (sub & 31)) & 1u) table_add_checked(table + ((size_t)b << kSliceBits) + ((v >> 3) & geo.low_mask), 1u, sat);
+                if (cnt[sub] > (uint32_t)kSplitCap) table_add_checked(table + ((size_t)b << kSliceBits) + ((v >> 3) & geo.low_mask), 1u, sat);
             }
         }
-        __syncthreads();
     }
+    if (threadIdx.x < kSubFan) bulk_wait_all(); // the rows must outlive the copies
 }
 
 // chunks per sub-region -> exclusive scan (one CTA; n_sub <= 16384)

@@ -648,7 +648,7 @@ def test_streamed_batches_equal_one_batch_equal_oracle(tmp_path, oracle, batch_b
     names, abd, tnf = oracle.featurize(path, None)
     ctx = _ctx()
     n_batches = len(list(_lib.FastqStream(path, target_seq_bytes=batch_bytes)))
-    assert n_batches > 3 if batch_bytes < 10 ** 6 else n_batches == 1
+    assert n_batches > 1 if batch_bytes < 10 ** 6 else n_batches == 1
     g_names, feats = stream.extract_features_streaming(
         ctx, lambda: _lib.FastqStream(path, pinned=True, target_seq_bytes=batch_bytes), resident_fraction=resident)
     g_abd, g_tnf = feats.raw()
@@ -681,14 +681,14 @@ def test_feature_streams_gzip_and_paired_input(tmp_path, oracle):
 
 
 def test_data_from_device_features_applies_the_csv_rounding(tmp_path, oracle):
-    """KAT-5 through the drop-in: a cloud with a tally >= 10^6 (bin 0 of a 7 000-pair cloud over a large genome).  The reference
+    """KAT-5 through the drop-in: clouds with a tally >= 10^6 (bin 0 of 8 000-pair clouds at ~8x coverage).  The reference
     normalises what pandas read from 6-significant-digit text (count_kmer.cpp:211); Data(features=Feature.features) must too."""
     from pangaea_b200 import Data, Feature
 
-    data = synth.generate(n_barcodes=3, mean_pairs=7000, read_len=100, n_genomes=1, genome_len=6_000_000, frag_len=4_000_000, seed=9)
+    data = synth.generate(n_barcodes=3, mean_pairs=8000, read_len=100, n_genomes=1, genome_len=600_000, frag_len=600_000, seed=9)
     path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
     names, abd, tnf = oracle.featurize(path, None)
-    assert abd.max() >= 1_000_000 and abd.max() % 10 != 0, "the case must exercise the rounding"
+    assert abd.max() >= 1_000_000 and (abd.max(axis=1) % 10 != 0).any() and ((abd > 0).sum(axis=1) >= 2).all(), "the case must exercise the rounding"
     ft = Feature(_args(tmp_path, interleaved_reads=path), "unused")
     g_names, g_abd, g_tnf = ft.extract_features(write_cache=False)
     assert g_abd.dtype == np.float64 and np.array_equal(g_abd, oracle.text_round(abd)) and np.array_equal(g_tnf, oracle.text_round(tnf))
