@@ -549,23 +549,27 @@ def ingest_from_fastq(args, ctx, batch_data, cfg, n_pairs=20_000_000):
                                     first_pair=p0, append=p0 > 0)
         del host
         size = os.path.getsize(path)
-        best = None
-        for _ in range(3):  # first pass warms the page cache, the pinned-buffer pool and the ctx workspaces
-            t0 = time.perf_counter()
-            names, f = stream.extract_features_streaming(ctx, lambda: _lib.FastqStream(path, pinned=True, target_seq_bytes=1 << 30))
-            f.normalized()
-            t1 = time.perf_counter()
-            rows = f.rows
-            f.free()
-            if best is None or t1 - t0 < best:
-                best = t1 - t0
-        t0 = time.perf_counter()
-        fq = _lib.Fastq(path, pinned=True)
-        parse_s = time.perf_counter() - t0
-        fq.close()
-    return {"value": round(2 * n / best, 1), "unit": UNIT, "seconds": round(best, 3), "parse_only_s": round(parse_s, 3),
-            "file_GB": round(size / 1e9, 3), "parse_GBps": round(size / 1e9 / parse_s, 2), "host_threads": os.cpu_count(), "rows": rows,
-            "sample": f"first {n} pairs of the batch as a plain-text interleaved FASTQ on local disk (page cache), streamed in 1 GiB batches, best of 3"}
+        res = {}
+        for name, run in (("device_ingest", lambda: stream.extract_features_device_ingest(ctx, path, window_bytes=1 << 30)),
+                          ("host_parser", lambda: stream.extract_features_streaming(ctx, lambda: _lib.FastqStream(path, pinned=True, target_seq_bytes=1 << 30)))):
+            best = None
+            try:
+                for _ in range(3):  # first pass warms the page cache, the pinned buffers and the ctx workspaces
+                    t0 = time.perf_counter()
+                    names, f = run()
+                    f.normalized()
+                    t1 = time.perf_counter()
+                    rows = f.rows
+                    f.free()
+                    best = t1 - t0 if best is None else min(best, t1 - t0)
+                res[name] = {"reads_per_s": round(2 * n / best, 1), "seconds": round(best, 3), "file_GBps": round(size / 1e9 / best, 2), "rows": rows}
+            except Exception as e:
+                res[name] = {"reads_per_s": None, "error": str(e)[:200]}
+    ok = [v["reads_per_s"] for v in res.values() if v.get("reads_per_s")]
+    return {"value": max(ok) if ok else None, "unit": UNIT, "paths": res, "file_GB": round(size / 1e9, 3), "host_threads": os.cpu_count(),
+            "sample": f"first {n} pairs of the batch as a plain-text interleaved FASTQ on local disk (page cache) -> normalised matrices on the host, "
+                      f"1 GiB windows, best of 3.  device_ingest: raw text staged to pinned memory and parsed in HBM (pg_ingest_text); "
+                      f"host_parser: csrc/fastq.cpp on all host cores (the path for gzip / paired / hostile input)"}
 
 
 def cpu_baseline_from_batch(args, batch_data, cfg):

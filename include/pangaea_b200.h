@@ -113,6 +113,9 @@ int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep_partition,
  * on the device for the featurize pass. */
 int pg_batch_compact(pg_ctx* ctx, pg_batch* b);
 int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE flags */
+/* shape of a batch and its arrays back on the host (tests, debugging; a compacted batch has no bases left: seq_out must be NULL) */
+void pg_batch_shape(const pg_batch* b, int64_t* n_reads, int64_t* n_bytes);
+int pg_batch_download(pg_ctx* ctx, const pg_batch* b, uint8_t* seq_out, int64_t* read_off_out, uint8_t* read_flag_out);
 
 /* ---- step 1a: global canonical k-mer counts --------------------------------- */
 /* replaces `jellyfish count -C -m k` (+ `dump`), feature.py:76-94,103, and the dump
@@ -210,12 +213,38 @@ int64_t pg_fastq_group_labels(const pg_fastq* fq, char* buf, int64_t cap, int64_
  * the clouds that START in its byte range; lines_before_lo = number of '\n' in [0, byte_lo) (pg_fastq_count_lines,
  * summed over the lower ranks) - record boundaries are line numbers 0 mod 8. */
 typedef struct pg_fastq_stream pg_fastq_stream;
+int pg_parallel_memcpy(void* dst, const void* src, int64_t n); /* all host cores: file mapping -> pinned staging buffer */
 int pg_fastq_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int64_t* n_newlines);
 int pg_fastq_stream_open(const char* path1, const char* path2, int flags, int64_t byte_lo, int64_t byte_hi, int64_t lines_before_lo,
                          pg_fastq_stream** out);
 /* *out = NULL at the end of the stream; target_seq_bytes <= 0: everything that is left */
 int pg_fastq_stream_next(pg_fastq_stream* s, int64_t target_seq_bytes, pg_fastq** out);
 void pg_fastq_stream_close(pg_fastq_stream* s);
+
+/* ---- FASTQ text on the device -------------------------------- */
+/* Replaces the host loop count_kmer.cpp:236-282 + getBarcode (count_kmer.cpp:25-53) for plain-text INTERLEAVED input: the
+ * text goes to HBM as it is, a line index is built there, headers are parsed there (read type latched by the first
+ * decisive header, "0_0_0", npos wrap-around and all), and the packed batch comes out without the bases ever being
+ * touched by the host.  text: a chunk that starts at a record boundary (line number 0 mod 8).  The batch ends at the
+ * last cloud flush inside the chunk (or at its end when the open cloud is labelled "" or PG_INGEST_FINAL is set);
+ * *consumed = bytes of `text` the batch covers - the caller starts the next chunk there.  consumed = 0 and *batch = NULL:
+ * the chunk holds no flush, pass a larger one.  last_barcode / *read_type_io carry the reference's two pieces of
+ * sequential state from chunk to chunk ("" and 0 at the start of a file; afterwards: the last label of the previous
+ * chunk and the value left in *read_type_io). */
+enum { PG_INGEST_FINAL = 1, PG_INGEST_DEVICE_TEXT = 2 };
+typedef struct pg_ingest pg_ingest; /* labels / keep flags of the clouds of one ingested batch; label 0 = last_barcode */
+int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, int flags, const char* last_barcode, int64_t last_len,
+                   int32_t* read_type_io, int64_t* consumed, pg_batch** batch, pg_ingest** info);
+int64_t pg_ingest_n_groups(const pg_ingest* info);
+const uint8_t* pg_ingest_group_keep(const pg_ingest* info);
+int64_t pg_ingest_group_labels(const pg_ingest* info, char* buf, int64_t cap, int64_t* offsets); /* as pg_fastq_group_labels */
+void pg_ingest_free(pg_ingest* info);
+/* Replaces `awk ... | LANG=C sort -k1,1 | cut -f2- | tr "\t" "\n"` (src/run_pangaea:237-252): the interleaved FASTQ in
+ * `in` sorted by its BX:Z: tag (untagged pairs last, "~~~"), ties broken by the rest of the record's text exactly as
+ * GNU sort's last-resort comparison does, tabs turned into newlines as the script's `tr` does.  Radix sort on the
+ * device; *n_out = bytes needed (nothing is written when out_cap is smaller).  Input must be whole 8-line records whose
+ * first line starts with '@' (PG_ERR_INVALID otherwise). */
+int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_in, char* out, int64_t out_cap, int64_t* n_out);
 
 /* ---- synthetic reads on device (bench input) --------------------- */
 /* fills DEVICE buffers shaped like a pg_reads batch: n_pairs pairs of 2 x read_len,

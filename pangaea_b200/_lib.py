@@ -57,6 +57,9 @@ SIGNATURES = {
     "pg_batch_adopt": (_int, [_vp, _P(pg_reads), _P(_vp)]),
     "pg_batch_free": (None, [_vp, _vp]),
     "pg_batch_n_groups": (_i64, [_vp]),
+    "pg_batch_shape": (None, [_vp, _P(_i64), _P(_i64)]),
+    "pg_batch_download": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pg_parallel_memcpy": (_int, [_vp, _vp, _i64]),
     "pg_count": (_int, [_vp, _vp]),
     "pg_count2": (_int, [_vp, _vp, _int]),
     "pg_batch_upload_count": (_int, [_vp, _P(pg_reads), _int, _P(_vp)]),
@@ -95,6 +98,12 @@ SIGNATURES = {
     "pg_fastq_group_label": (C.c_char_p, [_vp, _i64]),
     "pg_fastq_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
     "pg_mem_info": (_int, [_vp, _P(_i64), _P(_i64)]),
+    "pg_ingest_text": (_int, [_vp, _vp, _i64, _int, C.c_char_p, _i64, _P(_i32), _P(_i64), _P(_vp), _P(_vp)]),
+    "pg_ingest_n_groups": (_i64, [_vp]),
+    "pg_ingest_group_keep": (_vp, [_vp]),
+    "pg_ingest_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
+    "pg_ingest_free": (None, [_vp]),
+    "pg_fastq_sort_by_barcode": (_int, [_vp, _vp, _i64, _vp, _i64, _P(_i64)]),
     "pg_synth_generate": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _vp, _vp, _vp]),
     "pg_synth_generate2": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _i64, _i64, _vp, _vp, _vp]),
     "pg_timing_reset": (_int, [_vp]),
@@ -291,6 +300,19 @@ class Batch:
     def __init__(self, ctx: "Context", handle, keepalive=None):
         self.ctx, self.h, self._keep = ctx, handle, keepalive
 
+    def shape(self):
+        nr, nb = _i64(), _i64()
+        lib().pg_batch_shape(self.h, C.byref(nr), C.byref(nb))
+        return int(nr.value), int(nb.value)
+
+    def download(self, want_seq=True):
+        """(seq uint8[n_bytes] | None, read_off int64[n_reads + 1], read_flag uint8[n_reads]) copied back to the host"""
+        nr, nb = self.shape()
+        seq = np.empty(nb, dtype=np.uint8) if want_seq else None
+        off, flag = np.empty(nr + 1, dtype=np.int64), np.empty(nr, dtype=np.uint8)
+        self.ctx._ck(lib().pg_batch_download(self.ctx.h, self.h, seq.ctypes.data if want_seq and nb else None, off.ctypes.data, flag.ctypes.data if nr else None))
+        return seq, off, flag
+
     def compact(self):
         """drop the ASCII bases (and a kept partition); the packed stream stays for pg_featurize"""
         self.ctx._ck(lib().pg_batch_compact(self.ctx.h, self.h))
@@ -483,6 +505,42 @@ class Context:
         h = _vp()
         self._ck(lib().pg_features_from_raw(self.h, abd.ctypes.data, tnf.ctypes.data, abd.shape[0], abd.shape[1], tnf.shape[1], C.byref(h)))
         return Features(self, h)
+
+    # ---- FASTQ text on the device ---------------------------------------------
+    def ingest_text(self, text, last_barcode=b"", read_type=0, final=True, device_text=False, n_bytes=None):
+        """Device parse of a chunk of interleaved FASTQ text -> (Batch | None, labels list[str], keep uint8[], consumed, read_type)."""
+        n = int(n_bytes if n_bytes is not None else len(text))
+        rt, consumed, hb, hi = _i32(int(read_type)), _i64(0), _vp(), _vp()
+        flags = (1 if final else 0) | (2 if device_text else 0)
+        if isinstance(text, (bytes, bytearray)):
+            holder = np.frombuffer(text, dtype=np.uint8)
+            addr = holder.ctypes.data if n else None
+        else:
+            holder, addr = text, _ptr(text)
+        lb = bytes(last_barcode)
+        self._ck(lib().pg_ingest_text(self.h, addr, n, flags, lb, len(lb), C.byref(rt), C.byref(consumed), C.byref(hb), C.byref(hi)))
+        if not hb.value:
+            return None, [], np.zeros(0, np.uint8), 0, int(rt.value)
+        L = lib()
+        ng = int(L.pg_ingest_n_groups(hi))
+        keep = np.ctypeslib.as_array(C.cast(L.pg_ingest_group_keep(hi), C.POINTER(C.c_uint8)), shape=(ng,)).copy()
+        need = int(L.pg_ingest_group_labels(hi, None, 0, None))
+        buf = np.empty(max(need, 1), dtype=np.uint8)
+        off = np.empty(ng + 1, dtype=np.int64)
+        L.pg_ingest_group_labels(hi, buf.ctypes.data, need, off.ctypes.data)
+        blob, o = buf[:need].tobytes(), off.tolist()
+        labels = [blob[o[g]:o[g + 1]].decode("utf-8", "surrogateescape") for g in range(ng)]
+        L.pg_ingest_free(hi)
+        return Batch(self, hb), labels, keep, int(consumed.value), int(rt.value)
+
+    def sort_fastq_by_barcode(self, text) -> bytes:
+        """run_pangaea:237-252 on the device: interleaved FASTQ text -> text sorted by BX:Z: tag."""
+        src = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+        n = len(src)
+        out = np.empty(n + n // 64 + 16, dtype=np.uint8)  # tabs become newlines 1:1; a missing last newline adds one byte
+        got = _i64(0)
+        self._ck(lib().pg_fastq_sort_by_barcode(self.h, src.ctypes.data if n else None, n, out.ctypes.data, len(out), C.byref(got)))
+        return out[: got.value].tobytes()
 
     # ---- instrumentation -------------------------------------------------------
     def timing_reset(self):

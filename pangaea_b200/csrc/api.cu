@@ -77,6 +77,8 @@ struct pg_ctx {
     int64_t* d_scalar = nullptr; // 8 x int64 device scalars
     Workspace ws_entries, ws_entries2, ws_feat; // level-1 / level-2 entries of the count pass, entries of an unshared featurize pass
     BigCache big;
+    Workspace ws_text[2];                       // device staging of the text chunks of pg_ingest_text: filled on the copy stream while
+    int text_toggle = 0;                        // the compute stream still works on the batch before (two, used alternately)
     Workspace ws_stash;                         // one cached shared-partition buffer (taken by a batch in pg_count, returned by pg_batch_free)
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
@@ -417,6 +419,7 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     for (auto e : ctx->pool) cudaEventDestroy(e);
     for (auto& kv : ctx->big.free_blocks) cudaFree(kv.second); // (live blocks belong to batches / feature sets still around)
     cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p); cudaFree(ctx->ws_stash.p);
+    cudaFree(ctx->ws_text[0].p); cudaFree(ctx->ws_text[1].p);
     cudaFree(ctx->counts); cudaFree(ctx->slots); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_sat); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -592,6 +595,24 @@ extern "C" int pg_batch_adopt(pg_ctx* ctx, const pg_reads* d, pg_batch** out)
     rc = pack_batch(ctx, b);
     if (rc) { pg_batch_free(ctx, b); return rc; }
     *out = b;
+    return PG_OK;
+}
+
+extern "C" void pg_batch_shape(const pg_batch* b, int64_t* n_reads, int64_t* n_bytes)
+{
+    if (n_reads) *n_reads = b ? b->n_reads : -1;
+    if (n_bytes) *n_bytes = b ? b->n_bytes : -1;
+}
+
+extern "C" int pg_batch_download(pg_ctx* ctx, const pg_batch* b, uint8_t* seq_out, int64_t* read_off_out, uint8_t* read_flag_out)
+{
+    if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "pg_batch_download: bad argument");
+    if (seq_out && !b->seq) return fail(ctx, PG_ERR_STATE, "pg_batch_download: the batch was compacted, its bases are gone");
+    CK(cudaSetDevice(ctx->p.device));
+    if (seq_out && b->n_bytes) CK(cudaMemcpyAsync(seq_out, b->seq, (size_t)b->n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (read_off_out) CK(cudaMemcpyAsync(read_off_out, b->read_off, ((size_t)b->n_reads + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (read_flag_out && b->n_reads) CK(cudaMemcpyAsync(read_flag_out, b->read_flag, (size_t)b->n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
 }
 
@@ -1678,3 +1699,5 @@ extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len,
     return pg_synth_generate2(ctx, n_pairs, read_len, n_barcodes, d_bc_start, d_bc_genome, genome_len, frag_len, insert, sub_rate, n_rate, seed, 0, 0,
                               d_seq, d_read_off, d_read_flag);
 }
+
+#include "ingest_api.cuh"

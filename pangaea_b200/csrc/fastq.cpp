@@ -741,6 +741,20 @@ int next_sequential(pg_fastq_stream* s, int64_t target, pg_fastq** out)
 
 } // namespace
 
+// dst[0..n) = src[0..n) with all host cores (file mapping -> pinned staging buffer of the device ingest)
+extern "C" int pg_parallel_memcpy(void* dst, const void* src, int64_t n)
+{
+    if (n < 0 || (n && (!dst || !src))) return PG_ERR_INVALID;
+    try {
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(parallel_threads(), n / (4 << 20) + 1));
+        run_threads(T, [&](int t) {
+            const int64_t lo = n / T * t, hi = t + 1 == T ? n : n / T * (t + 1);
+            memcpy((char*)dst + lo, (const char*)src + lo, (size_t)(hi - lo));
+        });
+        return PG_OK;
+    } catch (...) { return PG_ERR_IO; }
+}
+
 extern "C" int pg_fastq_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int64_t* n_newlines)
 {
     if (!path || !n_newlines || byte_lo < 0) return PG_ERR_INVALID;

@@ -1,0 +1,375 @@
+// ingest_api.cuh - C-ABI over ingest.cuh (included at the end of api.cu: it uses the ctx internals).
+#pragma once
+#include "ingest.cuh"
+
+// exclusive scan of n int64 values (in -> out, may alias); *total (device, may be null) receives the sum
+static int scan64(pg_ctx* ctx, const long long* in, int64_t n, long long* out, long long* d_total)
+{
+    const int64_t n_tiles = std::max<int64_t>(1, (n + kScan64Tile - 1) / kScan64Tile);
+    long long* tile = nullptr;
+    CK(dmalloc(ctx, &tile, (size_t)n_tiles));
+    scan64_reduce_kernel<<<(int)n_tiles, kScan64Threads, 0, ctx->stream>>>(in, n, tile);
+    scan64_tiles_kernel<<<1, kScan64Threads, 0, ctx->stream>>>(tile, n_tiles, d_total);
+    scan64_apply_kernel<<<(int)n_tiles, kScan64Threads, 0, ctx->stream>>>(in, n, tile, out);
+    CK(cudaGetLastError());
+    dfree(ctx, tile);
+    return PG_OK;
+}
+
+// line index of a device text: line_start (n_lines + 1 entries, caller frees with dfree) and the line count
+static int build_line_index(pg_ctx* ctx, const uint8_t* d_text, int64_t n, long long** line_start_out, int64_t* n_lines_out)
+{
+    *line_start_out = nullptr; *n_lines_out = 0;
+    const int64_t n_tiles = std::max<int64_t>(1, (n + kTextTile - 1) / kTextTile);
+    long long *tile = nullptr, *d_total = (long long*)ctx->d_scalar;
+    CK(dmalloc(ctx, &tile, (size_t)n_tiles));
+    nl_count_kernel<<<(int)n_tiles, 256, 0, ctx->stream>>>(d_text, n, tile);
+    const int64_t n_t2 = std::max<int64_t>(1, (n_tiles + kScan64Tile - 1) / kScan64Tile);
+    long long* t2 = nullptr;
+    CK(dmalloc(ctx, &t2, (size_t)n_t2));
+    scan64_reduce_kernel<<<(int)n_t2, kScan64Threads, 0, ctx->stream>>>(tile, n_tiles, t2);
+    scan64_tiles_kernel<<<1, kScan64Threads, 0, ctx->stream>>>(t2, n_t2, d_total);
+    scan64_apply_kernel<<<(int)n_t2, kScan64Threads, 0, ctx->stream>>>(tile, n_tiles, t2, tile);
+    CK(cudaGetLastError());
+    uint8_t last = '\n';
+    CK(cudaMemcpyAsync(ctx->h_pin, d_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n > 0) CK(cudaMemcpyAsync(ctx->h_pin + 1, d_text + n - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t newlines = ctx->h_pin[0];
+    if (n > 0) last = *(const uint8_t*)(ctx->h_pin + 1);
+    const int64_t n_lines = newlines + ((n > 0 && last != '\n') ? 1 : 0);
+    long long* ls = nullptr;
+    CK(dmalloc(ctx, &ls, (size_t)n_lines + 2));
+    const long long zero = 0;
+    CK(cudaMemcpyAsync(ls, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
+    nl_fill_kernel<<<(int)n_tiles, 256, 0, ctx->stream>>>(d_text, n, tile, ls);
+    if (n > 0 && last != '\n') { // unterminated last line: a virtual newline at n
+        const long long end = n + 1;
+        CK(cudaMemcpyAsync(ls + n_lines, &end, sizeof(end), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream)); // (`zero` / `end` are stack variables)
+    dfree(ctx, tile); dfree(ctx, t2);
+    *line_start_out = ls; *n_lines_out = n_lines;
+    return PG_OK;
+}
+
+struct pg_ingest {
+    std::vector<std::string> labels;
+    std::vector<uint8_t> keep;
+};
+
+extern "C" void pg_ingest_free(pg_ingest* g) { delete g; }
+extern "C" int64_t pg_ingest_n_groups(const pg_ingest* g) { return g ? (int64_t)g->labels.size() : -1; }
+extern "C" const uint8_t* pg_ingest_group_keep(const pg_ingest* g) { return g ? g->keep.data() : nullptr; }
+extern "C" int64_t pg_ingest_group_labels(const pg_ingest* g, char* buf, int64_t cap, int64_t* offsets)
+{
+    if (!g) return -1;
+    int64_t need = 0;
+    for (auto& l : g->labels) need += (int64_t)l.size();
+    if (!buf || !offsets || cap < need) return need;
+    int64_t at = 0;
+    size_t i = 0;
+    for (auto& l : g->labels) { offsets[i++] = at; memcpy(buf + at, l.data(), l.size()); at += (int64_t)l.size(); }
+    offsets[i] = at;
+    return need;
+}
+
+// Device-side replacement of the host FASTQ loop for plain-text INTERLEAVED input (count_kmer.cpp:236-282 + getBarcode):
+// text (host or device memory) -> a packed pg_batch + the labels of its clouds.  See include/pangaea_b200.h.
+extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, int flags, const char* last_barcode, int64_t last_len,
+                              int32_t* read_type_io, int64_t* consumed_out, pg_batch** batch_out, pg_ingest** info_out)
+{
+    if (!ctx || !batch_out || !info_out || !consumed_out || !read_type_io || n_bytes < 0 || (n_bytes && !text) || last_len < 0 || (last_len && !last_barcode))
+        return fail(ctx, PG_ERR_INVALID, "pg_ingest_text: bad argument");
+    *batch_out = nullptr; *info_out = nullptr; *consumed_out = 0;
+    CK(cudaSetDevice(ctx->p.device));
+    const bool final_chunk = flags & PG_INGEST_FINAL, on_device = flags & PG_INGEST_DEVICE_TEXT;
+    const bool want_q = ctx->p.min_qual_char != 0;
+    uint8_t* d_text = nullptr;
+    std::vector<void*> tmp; // device temporaries, released on every path
+    auto done = [&](int rc) {
+        for (void* p : tmp) dfree(ctx, p);
+        return rc;
+    };
+#define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    if (on_device) d_text = (uint8_t*)const_cast<void*>(text);
+    else {
+        // The chunk crosses PCIe on the copy stream into a staging buffer of its own, so the copy runs next to whatever the
+        // compute stream still does for the previous batch (its count pass).  The buffer's last user was the ingest call
+        // two chunks back, which returned after a stream sync: nothing to wait for.
+        Workspace& w = ctx->ws_text[ctx->text_toggle];
+        ctx->text_toggle ^= 1;
+        if (w.bytes < (size_t)n_bytes + 64) {
+            if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+            const size_t want = (size_t)n_bytes + (size_t)n_bytes / 8 + 64;
+            CKI(cudaMalloc(&w.p, want));
+            w.bytes = want;
+        }
+        d_text = (uint8_t*)w.p;
+        cudaEvent_t ev = Timed::get(ctx);
+        CKI(cudaMemcpyAsync(d_text, text, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CKI(cudaEventRecord(ev, ctx->copy_stream));
+        CKI(cudaStreamWaitEvent(ctx->stream, ev, 0));
+        ctx->pool.push_back(ev);
+    }
+    long long* line_start = nullptr;
+    int64_t n_lines = 0;
+    int rc = build_line_index(ctx, d_text, n_bytes, &line_start, &n_lines);
+    if (rc) return done(rc);
+    tmp.push_back(line_start);
+    // whole records only, unless this is the end of the input (a trailing partial record still yields its reads)
+    int64_t n_rec = final_chunk ? (n_lines + 7) / 8 : n_lines / 8;
+    if (!final_chunk) { // complete lines only: an unterminated last line belongs to the next chunk
+        CKI(cudaMemcpyAsync(ctx->h_pin, d_text + std::max<int64_t>(n_bytes - 1, 0), 1, cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        if (n_bytes > 0 && *(const uint8_t*)ctx->h_pin != '\n') n_rec = (n_lines - 1) / 8;
+    }
+    TextLines T = { d_text, line_start, n_lines };
+    pg_ingest* info = new pg_ingest();
+    info->labels.emplace_back(last_barcode ? std::string(last_barcode, (size_t)last_len) : std::string());
+    auto finish_empty = [&]() {
+        info->keep.assign(1, info->labels[0].empty() ? 0 : 1);
+        pg_reads none = {};
+        pg_batch* b = nullptr;
+        int rc2 = alloc_batch(ctx, &none, &b);
+        if (!rc2) { cudaMemsetAsync(b->read_off, 0, sizeof(int64_t), ctx->stream); rc2 = pack_range(ctx, b, 0, b->n_words + 2); }
+        if (rc2) { delete info; if (b) pg_batch_free(ctx, b); return done(rc2); }
+        *batch_out = b; *info_out = info;
+        return done(PG_OK);
+    };
+    if (n_rec == 0) {
+        if (final_chunk) return finish_empty();
+        delete info; // not even one whole record in this chunk: the caller widens it
+        return done(PG_OK);
+    }
+
+    // ---- read type (latched once per FILE) and barcodes ----
+    unsigned long long latch = ~0ull;
+    if (*read_type_io) latch = (unsigned long long)*read_type_io; // record 0, known type
+    else {
+        unsigned long long* d_latch = (unsigned long long*)ctx->d_scalar;
+        CKI(cudaMemsetAsync(d_latch, 0xFF, sizeof(unsigned long long), ctx->stream));
+        latch_kernel<<<(int)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(T, 8, n_rec, d_latch);
+        CKI(cudaMemcpyAsync(ctx->h_pin, d_latch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        latch = (unsigned long long)ctx->h_pin[0];
+    }
+    long long *bc_off = nullptr, *read_bytes = nullptr, *read_start = nullptr, *change = nullptr, *change_rank = nullptr;
+    int32_t* bc_len = nullptr;
+    uint8_t *flag2 = nullptr, *d_carry = nullptr;
+    CKI(dmalloc(ctx, &bc_off, (size_t)n_rec)); tmp.push_back(bc_off);
+    CKI(dmalloc(ctx, &bc_len, (size_t)n_rec)); tmp.push_back(bc_len);
+    CKI(dmalloc(ctx, &read_bytes, (size_t)2 * n_rec)); tmp.push_back(read_bytes);
+    CKI(dmalloc(ctx, &read_start, (size_t)2 * n_rec + 1)); tmp.push_back(read_start);
+    CKI(dmalloc(ctx, &change, (size_t)n_rec)); tmp.push_back(change);
+    CKI(dmalloc(ctx, &change_rank, (size_t)n_rec)); tmp.push_back(change_rank);
+    CKI(dmalloc(ctx, &flag2, (size_t)2 * n_rec)); tmp.push_back(flag2);
+    CKI(dmalloc(ctx, &d_carry, (size_t)last_len + 1)); tmp.push_back(d_carry);
+    if (last_len) CKI(cudaMemcpyAsync(d_carry, last_barcode, (size_t)last_len, cudaMemcpyHostToDevice, ctx->stream));
+    const int g_rec = (int)((n_rec + 255) / 256);
+    barcode_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, latch, bc_off, bc_len);
+    reads_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, bc_off, bc_len, d_carry, (int)last_len, read_bytes, flag2, change);
+    CKI(cudaGetLastError());
+
+    // ---- where does this batch end?  at the last cloud flush, or anywhere inside a cloud labelled "" ----
+    int64_t n_use = n_rec;
+    std::vector<long long> h_change;
+    {
+        h_change.resize((size_t)n_rec);
+        CKI(cudaMemcpyAsync(h_change.data(), change, (size_t)n_rec * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        if (!final_chunk) {
+            int64_t last_flush = -1;
+            for (int64_t r = n_rec - 1; r >= 0; --r) if (h_change[(size_t)r]) { last_flush = r; break; }
+            // barcode of the last record: empty -> the open cloud is labelled "" (dropped whole): cut at the end
+            int32_t last_bc_len = 0;
+            CKI(cudaMemcpy(&last_bc_len, bc_len + (n_rec - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+            if (last_bc_len != 0 && last_flush != n_rec - 1) n_use = last_flush + 1; // (0 when the chunk holds no flush: the caller widens it)
+        }
+    }
+    if (n_use == 0) { delete info; *consumed_out = 0; pg_batch* none = nullptr; *batch_out = none; *info_out = nullptr; return done(PG_OK); }
+
+    // ---- the batch: read offsets, sequence bytes, flags ----
+    const int64_t n_reads = 2 * n_use;
+    CKI(scan64(ctx, read_bytes, n_reads, read_start, (long long*)ctx->d_scalar) == PG_OK ? cudaSuccess : cudaErrorUnknown);
+    CKI(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CKI(cudaMemcpyAsync(ctx->h_pin + 1, line_start + std::min<int64_t>(n_use * 8, n_lines), sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CKI(cudaStreamSynchronize(ctx->stream));
+    const int64_t seq_bytes = ctx->h_pin[0];
+    *consumed_out = std::min<int64_t>(ctx->h_pin[1], n_bytes);
+    pg_reads shape = {};
+    shape.n_reads = n_reads; shape.n_bytes = seq_bytes;
+    shape.qual = want_q ? (const uint8_t*)1 : nullptr; // (alloc_batch only tests it)
+    pg_batch* b = nullptr;
+    rc = alloc_batch(ctx, &shape, &b);
+    if (rc) { delete info; return done(rc); }
+    CKI(cudaMemcpyAsync(b->read_off, read_start, (size_t)n_reads * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CKI(cudaMemcpyAsync(b->read_off + n_reads, ctx->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CKI(cudaMemcpyAsync(b->read_flag, flag2, (size_t)n_reads, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int g_copy = (int)((n_reads * 32 + 255) / 256);
+    copy_reads_kernel<<<g_copy, 256, 0, ctx->stream>>>(T, n_use, read_start, read_bytes, b->seq);
+    if (want_q) copy_quals_kernel<<<g_copy, 256, 0, ctx->stream>>>(T, n_use, read_start, read_bytes, b->qual);
+    CKI(cudaGetLastError());
+    rc = pack_range(ctx, b, 0, b->n_words + 2);
+    if (rc) { delete info; pg_batch_free(ctx, b); return done(rc); }
+
+    // ---- labels of the clouds this batch opens ----
+    int64_t n_lab = 0;
+    for (int64_t r = 0; r < n_use; ++r) n_lab += h_change[(size_t)r] != 0;
+    if (n_lab) {
+        long long *lab_off = nullptr, *lab_len = nullptr, *lab_start = nullptr;
+        uint8_t* blob = nullptr;
+        CKI(scan64(ctx, change, n_use, change_rank, nullptr) == PG_OK ? cudaSuccess : cudaErrorUnknown);
+        CKI(dmalloc(ctx, &lab_off, (size_t)n_lab)); tmp.push_back(lab_off);
+        CKI(dmalloc(ctx, &lab_len, (size_t)n_lab)); tmp.push_back(lab_len);
+        CKI(dmalloc(ctx, &lab_start, (size_t)n_lab)); tmp.push_back(lab_start);
+        label_spans_kernel<<<(int)((n_use + 255) / 256), 256, 0, ctx->stream>>>(n_use, change, change_rank, bc_off, bc_len, lab_off, lab_len);
+        CKI(scan64(ctx, lab_len, n_lab, lab_start, (long long*)ctx->d_scalar) == PG_OK ? cudaSuccess : cudaErrorUnknown);
+        CKI(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        const int64_t blob_bytes = ctx->h_pin[0];
+        CKI(dmalloc(ctx, &blob, (size_t)blob_bytes + 1)); tmp.push_back(blob);
+        label_copy_kernel<<<(int)((n_lab + 255) / 256), 256, 0, ctx->stream>>>(d_text, n_lab, lab_off, lab_len, lab_start, blob);
+        CKI(cudaGetLastError());
+        std::vector<char> h_blob((size_t)blob_bytes + 1);
+        std::vector<long long> h_start((size_t)n_lab), h_len((size_t)n_lab);
+        CKI(cudaMemcpyAsync(h_blob.data(), blob, (size_t)blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaMemcpyAsync(h_start.data(), lab_start, (size_t)n_lab * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaMemcpyAsync(h_len.data(), lab_len, (size_t)n_lab * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CKI(cudaStreamSynchronize(ctx->stream));
+        info->labels.reserve((size_t)n_lab + 1);
+        for (int64_t k = 0; k < n_lab; ++k) info->labels.emplace_back(h_blob.data() + h_start[(size_t)k], (size_t)h_len[(size_t)k]);
+    }
+    info->keep.resize(info->labels.size());
+    for (size_t g = 0; g < info->labels.size(); ++g) info->keep[g] = info->labels[g].empty() ? 0 : 1;
+    if (!*read_type_io && latch != ~0ull && (int64_t)(latch >> 2) < n_use) *read_type_io = (int32_t)(latch & 3ull);
+    CKI(cudaStreamSynchronize(ctx->stream));
+#undef CKI
+    *batch_out = b; *info_out = info;
+    return done(PG_OK);
+}
+
+// ---------------------------------------------------------------------------
+// barcode sort of an interleaved FASTQ held in host memory (run_pangaea:237-252)
+// ---------------------------------------------------------------------------
+extern "C" int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_in, char* out, int64_t out_cap, int64_t* n_out)
+{
+    if (!ctx || n_in < 0 || (n_in && !in) || !n_out || (out_cap && !out)) return fail(ctx, PG_ERR_INVALID, "pg_fastq_sort_by_barcode: bad argument");
+    *n_out = 0;
+    if (n_in == 0) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    std::vector<void*> tmp;
+    auto done = [&](int rc) { for (void* p : tmp) dfree(ctx, p); return rc; };
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    uint8_t* d_text = nullptr;
+    CKS(dmalloc(ctx, &d_text, (size_t)n_in + 64)); tmp.push_back(d_text);
+    CKS(cudaMemcpyAsync(d_text, in, (size_t)n_in, cudaMemcpyHostToDevice, ctx->stream));
+    long long* line_start = nullptr;
+    int64_t n_lines = 0;
+    int rc = build_line_index(ctx, d_text, n_in, &line_start, &n_lines);
+    if (rc) return done(rc);
+    tmp.push_back(line_start);
+    const int64_t n_rec = (n_lines + 7) / 8;
+    if (n_rec >= (1ll << 32)) return done(fail(ctx, PG_ERR_INVALID, "pg_fastq_sort_by_barcode: more than 2^32 records in one call"));
+    TextLines T = { d_text, line_start, n_lines };
+    SortRec* recs = nullptr;
+    long long *rec_bytes = nullptr, *out_start = nullptr, *sorted_bytes = nullptr;
+    uint8_t *keysT = nullptr, *tie = nullptr;
+    uint32_t *col_seen = nullptr, *perm_a = nullptr, *perm_b = nullptr, *d_flags = nullptr;
+    CKS(dmalloc(ctx, &recs, (size_t)n_rec)); tmp.push_back(recs);
+    CKS(dmalloc(ctx, &rec_bytes, (size_t)n_rec)); tmp.push_back(rec_bytes);
+    CKS(dmalloc(ctx, &sorted_bytes, (size_t)n_rec)); tmp.push_back(sorted_bytes);
+    CKS(dmalloc(ctx, &out_start, (size_t)n_rec + 1)); tmp.push_back(out_start);
+    CKS(dmalloc(ctx, &keysT, (size_t)n_rec * kSortKeyBytes)); tmp.push_back(keysT);
+    CKS(dmalloc(ctx, &tie, (size_t)n_rec)); tmp.push_back(tie);
+    CKS(dmalloc(ctx, &col_seen, (size_t)kSortKeyBytes * 256)); tmp.push_back(col_seen);
+    CKS(dmalloc(ctx, &perm_a, (size_t)n_rec)); tmp.push_back(perm_a);
+    CKS(dmalloc(ctx, &perm_b, (size_t)n_rec)); tmp.push_back(perm_b);
+    CKS(dmalloc(ctx, &d_flags, 2)); tmp.push_back(d_flags);
+    CKS(cudaMemsetAsync(col_seen, 0, (size_t)kSortKeyBytes * 256 * sizeof(uint32_t), ctx->stream));
+    CKS(cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
+    const int g_rec = (int)((n_rec + 255) / 256);
+    sort_tag_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, recs, rec_bytes, d_flags);
+    sort_keys_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, recs, keysT, col_seen);
+    iota_kernel<<<g_rec, 256, 0, ctx->stream>>>(perm_a, n_rec);
+    CKS(cudaGetLastError());
+    std::vector<uint32_t> h_seen((size_t)kSortKeyBytes * 256);
+    uint32_t h_flags[2] = { 0, 0 };
+    CKS(cudaMemcpyAsync(h_seen.data(), col_seen, h_seen.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CKS(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+    CKS(cudaStreamSynchronize(ctx->stream));
+    if (h_flags[0]) return done(fail(ctx, PG_ERR_INVALID, "pg_fastq_sort_by_barcode: the text is not a whole number of 8-line records that start with '@'"));
+    // LSD radix over the key columns, last column first; a column in which every record holds the same byte is skipped
+    const int64_t n_chunks = (n_rec + kRadixChunk - 1) / kRadixChunk;
+    long long* hist = nullptr;
+    CKS(dmalloc(ctx, &hist, (size_t)256 * n_chunks)); tmp.push_back(hist);
+    const int g_radix = (int)((n_chunks + kRadixWarps - 1) / kRadixWarps);
+    int passes = 0;
+    for (int j = kSortKeyBytes - 1; j >= 0; --j) {
+        int distinct = 0;
+        for (int v = 0; v < 256; ++v) distinct += h_seen[(size_t)j * 256 + v] != 0;
+        if (distinct <= 1) continue;
+        const uint8_t* col = keysT + (size_t)j * n_rec;
+        radix_hist_kernel<<<g_radix, kRadixWarps * 32, 0, ctx->stream>>>(col, perm_a, n_rec, n_chunks, hist);
+        rc = scan64(ctx, hist, 256 * n_chunks, hist, nullptr);
+        if (rc) return done(rc);
+        radix_scatter_kernel<<<g_radix, kRadixWarps * 32, 0, ctx->stream>>>(col, perm_a, n_rec, n_chunks, hist, perm_b);
+        std::swap(perm_a, perm_b);
+        ++passes;
+    }
+    CKS(cudaGetLastError());
+    // records whose first kSortKeyBytes bytes tie are ordered by the rest of the line on the host
+    sort_ties_kernel<<<g_rec, 256, 0, ctx->stream>>>(keysT, perm_a, n_rec, tie, d_flags + 1);
+    CKS(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+    CKS(cudaStreamSynchronize(ctx->stream));
+    if (h_flags[1]) {
+        std::vector<uint32_t> h_perm((size_t)n_rec);
+        std::vector<uint8_t> h_tie((size_t)n_rec);
+        std::vector<long long> h_ls((size_t)n_lines + 1);
+        std::vector<SortRec> h_recs((size_t)n_rec);
+        CKS(cudaMemcpy(h_perm.data(), perm_a, (size_t)n_rec * 4, cudaMemcpyDeviceToHost));
+        CKS(cudaMemcpy(h_tie.data(), tie, (size_t)n_rec, cudaMemcpyDeviceToHost));
+        CKS(cudaMemcpy(h_ls.data(), line_start, ((size_t)n_lines + 1) * 8, cudaMemcpyDeviceToHost));
+        CKS(cudaMemcpy(h_recs.data(), recs, (size_t)n_rec * sizeof(SortRec), cudaMemcpyDeviceToHost));
+        auto cmp_string = [&](uint32_t r) { // the comparison string of record r
+            std::string s;
+            const SortRec& sr = h_recs[r];
+            if (sr.tag_len < 0) s = "~~~"; else s.assign(in + sr.tag_off, (size_t)sr.tag_len);
+            s += '\t';
+            const long long a = h_ls[(size_t)r * 8], e = h_ls[(size_t)std::min<int64_t>((int64_t)r * 8 + 8, n_lines)] - 1;
+            for (long long p = a; p < e; ++p) s += in[p] == '\n' ? '\t' : in[p];
+            return s;
+        };
+        for (int64_t i = 0; i < n_rec;) {
+            int64_t j2 = i + 1;
+            while (j2 < n_rec && h_tie[(size_t)j2]) ++j2;
+            if (j2 - i > 1) {
+                std::vector<std::pair<std::string, uint32_t>> grp;
+                for (int64_t k = i; k < j2; ++k) grp.emplace_back(cmp_string(h_perm[(size_t)k]), h_perm[(size_t)k]);
+                std::stable_sort(grp.begin(), grp.end(), [](const std::pair<std::string, uint32_t>& x, const std::pair<std::string, uint32_t>& y) { return x.first < y.first; });
+                for (int64_t k = i; k < j2; ++k) h_perm[(size_t)k] = grp[(size_t)(k - i)].second;
+            }
+            i = j2;
+        }
+        CKS(cudaMemcpy(perm_a, h_perm.data(), (size_t)n_rec * 4, cudaMemcpyHostToDevice));
+    }
+    // output: every record's bytes in sorted order
+    gather_len_kernel<<<g_rec, 256, 0, ctx->stream>>>(rec_bytes, perm_a, n_rec, sorted_bytes);
+    rc = scan64(ctx, sorted_bytes, n_rec, out_start, (long long*)ctx->d_scalar);
+    if (rc) return done(rc);
+    CKS(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CKS(cudaStreamSynchronize(ctx->stream));
+    const int64_t total = ctx->h_pin[0];
+    *n_out = total;
+    if (total > out_cap) return done(fail(ctx, PG_ERR_INVALID, "pg_fastq_sort_by_barcode: output buffer too small (need n_out bytes)"));
+    uint8_t* d_out = nullptr;
+    CKS(dmalloc(ctx, &d_out, (size_t)total + 64)); tmp.push_back(d_out);
+    sort_copy_kernel<<<(int)((n_rec * 32 + 255) / 256), 256, 0, ctx->stream>>>(T, n_rec, perm_a, out_start, d_out);
+    CKS(cudaGetLastError());
+    CKS(cudaMemcpyAsync(out, d_out, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    CKS(cudaStreamSynchronize(ctx->stream));
+    (void)passes;
+#undef CKS
+    return done(PG_OK);
+}

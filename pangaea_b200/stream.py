@@ -52,6 +52,86 @@ class _Prefetch:
             yield item
 
 
+class DeviceIngest:
+    """Batches of a plain-text INTERLEAVED FASTQ parsed ON THE DEVICE (csrc/ingest.cuh, pg_ingest_text): the host only
+    moves raw file bytes into a pinned staging buffer (all cores) and from there over PCIe; the line index, getBarcode,
+    the cloud flags and the 2-bit pack happen in HBM.  While the GPU works on window w the host stages window w + 1; the
+    part of w behind its last cloud flush (or an incomplete record) is put in front of it.
+
+    Iterating yields (Batch, keep uint8[], labels list[str], is_last_batch)."""
+
+    def __init__(self, ctx, path, window_bytes=1 << 30, slack_bytes=64 << 20):
+        self.ctx, self.path, self.window, self.slack = ctx, path, int(window_bytes), int(slack_bytes)
+
+    def __iter__(self):
+        import torch
+
+        ctx = self.ctx
+        n = _size(self.path)
+        if n == 0:
+            batch, labels, keep, _, _ = ctx.ingest_text(b"", b"", 0, final=True)
+            yield batch, keep, labels, True
+            return
+        mm = np.memmap(self.path, dtype=np.uint8, mode="r")
+        L = _lib.lib()
+        window, slack = self.window, self.slack
+        state = {}
+
+        def alloc():
+            state["bufs"] = [torch.empty(slack + window, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            state["views"] = [b.numpy() for b in state["bufs"]]
+
+        def stage(k, lo, hi):  # file bytes [lo, hi) -> views[k][slack : slack + hi - lo], all cores
+            if hi > lo:
+                L.pg_parallel_memcpy(state["views"][k][slack:].ctypes.data, mm[lo:hi].ctypes.data, hi - lo)
+
+        alloc()
+        last, rt = b"", 0
+        k, head = 0, 0                      # head: bytes in front of views[k][slack] that open the chunk (tail of the previous one)
+        lo, hi = 0, min(n, window)          # file range staged at views[k][slack:]
+        stage(k, lo, hi)
+        while True:
+            final = hi >= n
+            chunk = state["views"][k][slack - head: slack + (hi - lo)]
+            nxt, nlo, nhi = None, hi, min(n, hi + window)
+            if not final:                   # stage the next window while the GPU parses this one
+                nxt = threading.Thread(target=stage, args=(k ^ 1, nlo, nhi))
+                nxt.start()
+            batch, labels, keep, consumed, rt = ctx.ingest_text(chunk, last, rt, final=final, n_bytes=len(chunk))
+            if nxt:
+                nxt.join()
+            restart = None
+            if batch is None:               # no cloud flush inside the chunk (a cloud larger than the window): take a larger one
+                if final:
+                    raise _lib.PgError(-5, "device ingest made no progress on the last chunk")
+                window *= 2
+                restart = lo - head
+            else:
+                last = labels[-1].encode("utf-8", "surrogateescape")
+                yield batch, keep, labels, final
+                if final:
+                    return
+                tail = len(chunk) - consumed    # bytes of this chunk that the next batch starts with
+                if tail > slack:
+                    slack = 2 * tail
+                    restart = lo - head + consumed
+                else:
+                    if tail:
+                        state["views"][k ^ 1][slack - tail: slack] = chunk[consumed:]
+                    k, head, lo, hi = k ^ 1, tail, nlo, nhi
+            if restart is not None:         # rare: new buffers, staged synchronously from `restart`
+                del chunk
+                alloc()
+                k, head, lo, hi = 0, 0, restart, min(n, restart + window)
+                stage(k, lo, hi)
+
+
+def _size(path):
+    import os
+
+    return os.path.getsize(path)
+
+
 def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=True, reduce_table=None, resident_fraction=0.45):
     """Whole path over a stream of batches.
 
@@ -140,6 +220,57 @@ def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=Tru
             fq.close()
             parts.append(f)
         stream.close()
+    feats = ctx.concat_features(parts)
+    for f in parts:
+        f.free()
+    return names, feats
+
+
+def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 30, clear_table=True, reduce_table=None, resident_fraction=0.45):
+    """The same two-pass flow with the DEVICE parser (DeviceIngest) as the source of batches - plain-text interleaved FASTQ
+    only; gzip, paired or hostile input goes through extract_features_streaming.  Returns (names list[str], Features)."""
+    if clear_table:
+        ctx.table_clear()
+    _, total = ctx.mem_info()
+    budget = int(total * resident_fraction)
+    held, resident, keep_resident = [], 0, True
+    for batch, keep, labels, is_last in DeviceIngest(ctx, path, window_bytes):
+        single = is_last and not held
+        ctx.count(batch, keep_partition=single)
+        n_reads, n_bytes = batch.shape()
+        packed = n_bytes // 2 + 9 * n_reads
+        if keep_resident and not single and resident + packed > budget:
+            keep_resident = False
+            for hb in held:
+                hb[0].free()
+                hb[0] = None
+        if keep_resident:
+            if not single:
+                batch.compact()
+            resident += packed
+        else:
+            batch.free()
+            batch = None
+        held.append([batch, keep, labels])
+    if reduce_table:
+        reduce_table()
+    names, parts = [], []
+    if keep_resident:
+        for b, keep, labels in held:
+            f = ctx.featurize(b, keep)
+            names += [labels[g] for g in f.row_groups().tolist()]
+            b.free()
+            parts.append(f)
+    else:
+        for i, (b, keep, labels, _) in enumerate(DeviceIngest(ctx, path, window_bytes)):
+            if len(keep) != len(held[i][1]):
+                raise _lib.PgError(-5, "the input changed between the two passes")
+            f = ctx.featurize(b, keep)
+            names += [labels[g] for g in f.row_groups().tolist()]
+            b.free()
+            parts.append(f)
+    if len(parts) == 1:
+        return names, parts[0]
     feats = ctx.concat_features(parts)
     for f in parts:
         f.free()
