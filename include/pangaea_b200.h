@@ -246,6 +246,24 @@ void pg_ingest_free(pg_ingest* info);
  * first line starts with '@' (PG_ERR_INVALID otherwise). */
 int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_in, char* out, int64_t out_cap, int64_t* n_out);
 
+/* ---- step-2 input pipeline on the device ---------------------- */
+/* Replaces CustomWeightedRandomSampler (src/utils.py:11-23: numpy.random.choice(range(N), size, p = w / sum(w), replace)) and the
+ * DataLoader's row gather (src/data.py:27-31, src/pangaea.py:87-89).  The uniforms are the caller's (numpy's generator, so
+ * a seeded run draws what the reference draws); the cumulative sum (sequential, as numpy's), the binary searches, the
+ * first-occurrence filter of the draws without replacement and the gather of the batch rows run on the device.
+ * weights: host or device memory, n doubles; total = their sum as the reference computes it (torch.sum). */
+typedef struct pg_sampler pg_sampler;
+int pg_sampler_create(pg_ctx* ctx, const double* weights, int64_t n, double total, pg_sampler** out);
+void pg_sampler_free(pg_ctx* ctx, pg_sampler* s);
+/* replace = True: d_idx_out[j] (device, m x int64) = cdf.searchsorted(uniforms[j], side = "right"); uniforms in host memory */
+int pg_sampler_draw(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t* d_idx_out);
+/* replace = False, one round of numpy's loop: m = size - n_found fresh uniforms; the draws that are first occurrences are
+ * appended at d_idx_out[n_found ...] in draw order and their probabilities zeroed; *n_new = how many.  Loop until done. */
+int pg_sampler_draw_unique_round(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t n_found, int64_t* d_idx_out,
+                                 int64_t* n_new);
+/* rows d_idx[0..m) of the normalised matrices into device buffers [m, abd_dim] / [m, tnf_dim] (either may be NULL) */
+int pg_features_gather(pg_ctx* ctx, const pg_features* f, const int64_t* d_idx, int64_t m, float* d_abd_out, float* d_tnf_out);
+
 /* ---- synthetic reads on device (bench input) --------------------- */
 /* fills DEVICE buffers shaped like a pg_reads batch: n_pairs pairs of 2 x read_len,
  * (read_len + 1) bytes per read.  d_bc_start[n_barcodes + 1] = first pair of every

@@ -49,3 +49,34 @@ def barcode_sort(text: bytes) -> bytes:
     env = dict(os.environ, LANG="C", LC_ALL="C")
     p = subprocess.run("sort -k1,1 | cut -f2- | tr '\\t' '\\n'", shell=True, input=awk_tag_lines(text), stdout=subprocess.PIPE, env=env, check=True)
     return p.stdout
+
+
+def weighted_choice(weights, num_samples, replacement):
+    """CustomWeightedRandomSampler.__iter__ (src/utils.py:15-23) restated: numpy.random.choice(range(N), size, p, replace) of the
+    legacy RandomState, written out (numpy/random/mtrand.pyx: choice).  Consumes numpy's global generator like the reference.
+    PINNED: tests/golden/sampler/*.npz were produced by the reference's own class (tests/golden/make_golden_sampler.py)."""
+    import numpy as np
+    import torch
+
+    w = torch.as_tensor(weights, dtype=torch.double)
+    p = w.numpy() / torch.sum(w).numpy()
+    if replacement:
+        cdf = p.cumsum()
+        cdf /= cdf[-1]
+        return cdf.searchsorted(np.random.random_sample(num_samples), side="right").astype(np.int64)
+    p = p.copy()
+    found = np.zeros(num_samples, dtype=np.int64)
+    n_uniq = 0
+    while n_uniq < num_samples:
+        x = np.random.rand(num_samples - n_uniq)
+        if n_uniq > 0:
+            p[found[0:n_uniq]] = 0
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        new = cdf.searchsorted(x, side="right")
+        _, unique_indices = np.unique(new, return_index=True)
+        unique_indices.sort()
+        new = new.take(unique_indices)
+        found[n_uniq:n_uniq + new.size] = new
+        n_uniq += new.size
+    return found

@@ -104,6 +104,11 @@ SIGNATURES = {
     "pg_ingest_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
     "pg_ingest_free": (None, [_vp]),
     "pg_fastq_sort_by_barcode": (_int, [_vp, _vp, _i64, _vp, _i64, _P(_i64)]),
+    "pg_sampler_create": (_int, [_vp, _vp, _i64, C.c_double, _P(_vp)]),
+    "pg_sampler_free": (None, [_vp, _vp]),
+    "pg_sampler_draw": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pg_sampler_draw_unique_round": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _P(_i64)]),
+    "pg_features_gather": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "pg_synth_generate": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _vp, _vp, _vp]),
     "pg_synth_generate2": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i32, C.c_double, C.c_double, C.c_uint64, _i64, _i64, _vp, _vp, _vp]),
     "pg_timing_reset": (_int, [_vp]),

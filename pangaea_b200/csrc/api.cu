@@ -102,6 +102,7 @@ struct pg_batch {
     uint8_t *seq = nullptr, *qual = nullptr, *read_flag = nullptr;
     int64_t* read_off = nullptr;
     bool owns = false;
+    bool owns_meta = false; // read_off / read_flag are the batch's own copies although the bases were adopted (pg_batch_compact)
     int64_t n_reads = 0, n_bytes = 0, n_words = 0;
     uint64_t* codes = nullptr;
     uint32_t *maskF = nullptr, *maskC = nullptr;
@@ -633,6 +634,7 @@ extern "C" void pg_batch_free(pg_ctx* ctx, pg_batch* b)
     if (!b || !ctx) return;
     cudaSetDevice(ctx->p.device);
     if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); dfree(ctx, b->read_off); dfree(ctx, b->read_flag); }
+    else if (b->owns_meta) { dfree(ctx, b->read_off); dfree(ctx, b->read_flag); }
     dfree(ctx, b->codes); dfree(ctx, b->maskF); dfree(ctx, b->maskC);
     dfree(ctx, b->gstart); dfree(ctx, b->nofeat_len); dfree(ctx, b->maskR); dfree(ctx, b->wg);
     free_stash(ctx, b);
@@ -1605,7 +1607,19 @@ extern "C" int pg_batch_compact(pg_ctx* ctx, pg_batch* b)
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
     if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); }
-    b->seq = b->qual = nullptr; // (an adopted batch: the caller may release its buffers now)
+    else if (!b->owns_meta) {
+        // an adopted batch: the caller may release ALL its buffers now, so the read offsets and flags - which pg_featurize
+        // still needs - move into memory of the batch's own (9 B per read)
+        int64_t* off = nullptr;
+        uint8_t* flag = nullptr;
+        CK(dmalloc(ctx, &off, (size_t)b->n_reads + 1));
+        CK(dmalloc(ctx, &flag, (size_t)std::max<int64_t>(b->n_reads, 1)));
+        CK(cudaMemcpyAsync(off, b->read_off, ((size_t)b->n_reads + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (b->n_reads) CK(cudaMemcpyAsync(flag, b->read_flag, (size_t)b->n_reads, cudaMemcpyDeviceToDevice, ctx->stream));
+        b->read_off = off; b->read_flag = flag; b->owns_meta = true;
+        CK(cudaStreamSynchronize(ctx->stream)); // the caller's buffers are free to go when this returns
+    }
+    b->seq = b->qual = nullptr;
     free_stash(ctx, b);
     return PG_OK;
 }

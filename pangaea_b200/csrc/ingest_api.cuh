@@ -373,3 +373,124 @@ extern "C" int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_i
 #undef CKS
     return done(PG_OK);
 }
+
+// ---------------------------------------------------------------------------
+// step-2 input pipeline: weighted sampler + batch gather (sampler.cuh)
+// ---------------------------------------------------------------------------
+#include "sampler.cuh"
+
+struct pg_sampler {
+    int64_t n = 0;
+    double *p = nullptr, *cdf = nullptr;
+    unsigned long long* first = nullptr; // first-occurrence scratch of the draws without replacement (all ~0 between rounds)
+    bool cdf_valid = false;
+};
+
+extern "C" void pg_sampler_free(pg_ctx* ctx, pg_sampler* s)
+{
+    if (!s) return;
+    if (ctx) { cudaSetDevice(ctx->p.device); dfree(ctx, s->p); dfree(ctx, s->cdf); dfree(ctx, s->first); }
+    delete s;
+}
+
+extern "C" int pg_sampler_create(pg_ctx* ctx, const double* weights, int64_t n, double total, pg_sampler** out)
+{
+    if (!ctx || !out || n < 1 || !weights || !(total > 0.0)) return fail(ctx, PG_ERR_INVALID, "pg_sampler_create: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->p.device));
+    pg_sampler* s = new pg_sampler();
+    s->n = n;
+    double* d_w = nullptr;
+    cudaError_t e = dmalloc(ctx, &s->p, (size_t)n);
+    if (e == cudaSuccess) e = dmalloc(ctx, &s->cdf, (size_t)n);
+    if (e == cudaSuccess) e = dmalloc(ctx, &s->first, (size_t)n);
+    if (e == cudaSuccess) e = dmalloc(ctx, &d_w, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, weights, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream); // host or device weights
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->first, 0xFF, (size_t)n * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        sampler_prob_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(d_w, n, total, s->p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, d_w);
+    if (e != cudaSuccess) { pg_sampler_free(ctx, s); return fail(ctx, PG_ERR_CUDA, std::string("pg_sampler_create: ") + cudaGetErrorString(e)); }
+    *out = s;
+    return PG_OK;
+}
+
+static int sampler_refresh_cdf(pg_ctx* ctx, pg_sampler* s)
+{
+    sampler_cumsum_kernel<<<1, 1, 0, ctx->stream>>>(s->p, s->n, s->cdf);
+    if (s->n > 1) sampler_norm_kernel<<<(int)((s->n + 255) / 256), 256, 0, ctx->stream>>>(s->cdf, s->n);
+    sampler_norm_last_kernel<<<1, 1, 0, ctx->stream>>>(s->cdf, s->n);
+    CK(cudaGetLastError());
+    s->cdf_valid = true;
+    return PG_OK;
+}
+
+// with replacement: idx_out[j] = searchsorted(cdf, uniforms[j], "right").  uniforms: host memory; idx_out: device memory (m int64)
+extern "C" int pg_sampler_draw(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t* d_idx_out)
+{
+    if (!ctx || !s || m < 0 || (m && (!uniforms || !d_idx_out))) return fail(ctx, PG_ERR_INVALID, "pg_sampler_draw: bad argument");
+    if (!m) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    if (!s->cdf_valid) { int rc = sampler_refresh_cdf(ctx, s); if (rc) return rc; }
+    double* d_u = nullptr;
+    CK(dmalloc(ctx, &d_u, (size_t)m));
+    CK(cudaMemcpyAsync(d_u, uniforms, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    sampler_search_kernel<<<(int)((m + 255) / 256), 256, 0, ctx->stream>>>(s->cdf, s->n, d_u, m, d_idx_out);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_u);
+    return PG_OK;
+}
+
+// one round of numpy's choice(replace=False): m uniforms -> the first occurrences among the draws, appended at d_idx_out[n_found...];
+// *n_new = how many were appended.  The caller loops until it has `size` indices, drawing size - n_found fresh uniforms per round.
+extern "C" int pg_sampler_draw_unique_round(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t n_found, int64_t* d_idx_out,
+                                            int64_t* n_new)
+{
+    if (!ctx || !s || m < 1 || !uniforms || !d_idx_out || !n_new || n_found < 0) return fail(ctx, PG_ERR_INVALID, "pg_sampler_draw_unique_round: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    int rc = sampler_refresh_cdf(ctx, s); // the probabilities of the items found so far are zero by now
+    if (rc) return rc;
+    double* d_u = nullptr;
+    int64_t* d_new = nullptr;
+    long long *keep = nullptr, *rank = nullptr;
+    CK(dmalloc(ctx, &d_u, (size_t)m)); CK(dmalloc(ctx, &d_new, (size_t)m)); CK(dmalloc(ctx, &keep, (size_t)m)); CK(dmalloc(ctx, &rank, (size_t)m));
+    CK(cudaMemcpyAsync(d_u, uniforms, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int g = (int)((m + 255) / 256);
+    sampler_search_kernel<<<g, 256, 0, ctx->stream>>>(s->cdf, s->n, d_u, m, d_new);
+    sampler_first_kernel<<<g, 256, 0, ctx->stream>>>(d_new, m, s->first);
+    sampler_keep_kernel<<<g, 256, 0, ctx->stream>>>(d_new, m, s->first, keep);
+    rc = scan64(ctx, keep, m, rank, (long long*)ctx->d_scalar);
+    if (!rc) {
+        sampler_commit_kernel<<<g, 256, 0, ctx->stream>>>(d_new, m, keep, rank, n_found, d_idx_out, s->p, s->first);
+        s->cdf_valid = false;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *n_new = ctx->h_pin[0];
+    }
+    dfree(ctx, d_u); dfree(ctx, d_new); dfree(ctx, keep); dfree(ctx, rank);
+    return rc;
+}
+
+// batch gather on the device: rows idx[0..m) of the normalised matrices (pg_normalize first) into abd_out [m, v] / tnf_out [m, td]
+extern "C" int pg_features_gather(pg_ctx* ctx, const pg_features* f, const int64_t* d_idx, int64_t m, float* d_abd_out, float* d_tnf_out)
+{
+    if (!ctx || !f || m < 0 || (m && !d_idx)) return fail(ctx, PG_ERR_INVALID, "pg_features_gather: bad argument");
+    if (!f->normalized) return fail(ctx, PG_ERR_STATE, "call pg_normalize first");
+    if (!m) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    uint32_t* bad = (uint32_t*)ctx->d_scalar;
+    CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    const int g = (int)((m * 32 + 255) / 256);
+    if (d_abd_out) gather_rows_kernel<<<g, 256, 0, ctx->stream>>>(f->abd, f->vs, d_idx, m, f->rows, d_abd_out, bad);
+    if (d_tnf_out) gather_rows_kernel<<<g, 256, 0, ctx->stream>>>(f->tnf, f->td, d_idx, m, f->rows, d_tnf_out, bad);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pin, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*(const uint32_t*)ctx->h_pin) return fail(ctx, PG_ERR_INVALID, "pg_features_gather: row index out of range");
+    return PG_OK;
+}

@@ -769,3 +769,26 @@ def test_full_size_sliced_path_equals_direct_path(monkeypatch):
     assert a0.shape[0] > 400_000
     assert torch.equal(t0, t1), "k-mer tables differ"
     assert torch.equal(a0, a1) and torch.equal(n0, n1), "feature matrices differ"
+
+
+def test_compacted_adopted_batch_survives_the_callers_buffers():
+    """pg_batch_compact on an ADOPTED batch copies the read offsets / flags: the caller may free (and overwrite) its buffers
+    and pg_featurize still sees the batch (the streamed bench configurations rely on it)."""
+    import torch
+
+    ctx = _ctx()
+    s = synth.device_batch(ctx, 60_000, 100, n_barcodes=600, n_genomes=4, genome_len=200_000, seed=5)
+    keep = np.ones(s["n_groups"], np.uint8)
+    keep[0] = 0
+    b = ctx.adopt(s["reads"])
+    ctx.count(b, keep_partition=False)
+    want = ctx.featurize(b, keep).raw()
+    b.compact()
+    ctx.synchronize()
+    for t in ("_seq_full", "off", "flag", "seq"):
+        s[t].fill_(255 if s[t].dtype == torch.uint8 else -1)   # the caller recycles its memory
+    torch.cuda.synchronize()
+    got = ctx.featurize(b, keep).raw()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    with pytest.raises(_lib.PgError, match="compacted"):
+        b.download()
