@@ -213,7 +213,8 @@ int64_t pg_fastq_group_labels(const pg_fastq* fq, char* buf, int64_t cap, int64_
  * the clouds that START in its byte range; lines_before_lo = number of '\n' in [0, byte_lo) (pg_fastq_count_lines,
  * summed over the lower ranks) - record boundaries are line numbers 0 mod 8. */
 typedef struct pg_fastq_stream pg_fastq_stream;
-int pg_parallel_memcpy(void* dst, const void* src, int64_t n); /* all host cores: file mapping -> pinned staging buffer */
+int pg_parallel_memcpy(void* dst, const void* src, int64_t n); /* all host cores */
+int pg_parallel_pread(const char* path, int64_t offset, int64_t n, void* dst); /* all host cores: file -> (pinned) staging buffer */
 int pg_fastq_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int64_t* n_newlines);
 int pg_fastq_stream_open(const char* path1, const char* path2, int flags, int64_t byte_lo, int64_t byte_hi, int64_t lines_before_lo,
                          pg_fastq_stream** out);
@@ -245,6 +246,32 @@ void pg_ingest_free(pg_ingest* info);
  * device; *n_out = bytes needed (nothing is written when out_cap is smaller).  Input must be whole 8-line records whose
  * first line starts with '@' (PG_ERR_INVALID otherwise). */
 int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_in, char* out, int64_t out_cap, int64_t* n_out);
+
+/* ---- format converters and extract_reads on the device ---- */
+/* preprocess_stlfr -n [-l] (src/cpptools/preprocess_stlfr.cpp:76-115; run_pangaea:143 passes -n -l): headers `name#a_b_c/1`
+ * become `name\tBX:Z:a_b_c[-1]` (`name` alone when a or b is "0"), the identifier of file 1 going into BOTH outputs; all other
+ * lines are copied.  r1 / r2: the two FASTQ texts (host memory).  *n_out = bytes needed; PG_ERR_INVALID when a buffer is too
+ * small or when the reference tool would abort (no '#', barcode not a_b_c).  The whitelist mode (without -n) is not here. */
+int pg_preprocess_stlfr(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, int library, char* out1, int64_t cap1,
+                        int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2);
+/* preprocess_tellseq (src/cpptools/preprocess_tellseq.cpp:52-84): idx = the index reads (I1); records whose index read is not 18
+ * bases are dropped; header = R1 header up to the first ' ' + "\tBX:Z:" + index read + "-1" in both outputs, the third line
+ * always "+"; out_wl = the barcodes, one per line. */
+int pg_preprocess_tellseq(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, const char* idx, int64_t ni, char* out1,
+                          int64_t cap1, int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2, char* out_wl, int64_t cap_wl,
+                          int64_t* n_out_wl);
+/* extract_reads -i (src/cpptools/extract_reads.cpp:86-124): open parses the interleaved text on the device and reports its
+ * barcode runs (consecutive pairs with the same barcode; run 0 = pairs without barcode at the start); the caller maps every
+ * run label to a cluster index or -1 (the reference's barcode2cluster, extract_reads.cpp:58-84); route writes, per cluster
+ * and in file order, the .fq blob (header rewritten to name + "\tBX:Z:" + barcode + "-1") and the .barcode blob, and returns
+ * the n_clusters + 1 byte offsets of the clusters' slices; copy brings the two blobs to the host. */
+typedef struct pg_extract pg_extract;
+int pg_extract_open(pg_ctx* ctx, const char* text, int64_t n_bytes, pg_extract** out);
+int64_t pg_extract_n_runs(const pg_extract* x);
+int64_t pg_extract_run_labels(const pg_extract* x, char* buf, int64_t cap, int64_t* offsets);
+int pg_extract_route(pg_ctx* ctx, pg_extract* x, const int32_t* cluster_of_run, int32_t n_clusters, int64_t* fq_start, int64_t* bc_start);
+int pg_extract_copy(pg_ctx* ctx, const pg_extract* x, char* fq_out, char* bc_out);
+void pg_extract_close(pg_ctx* ctx, pg_extract* x);
 
 /* ---- step-2 input pipeline on the device ---------------------- */
 /* Replaces CustomWeightedRandomSampler (src/utils.py:11-23: numpy.random.choice(range(N), size, p = w / sum(w), replace)) and the

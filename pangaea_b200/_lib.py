@@ -104,6 +104,15 @@ SIGNATURES = {
     "pg_ingest_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
     "pg_ingest_free": (None, [_vp]),
     "pg_fastq_sort_by_barcode": (_int, [_vp, _vp, _i64, _vp, _i64, _P(_i64)]),
+    "pg_parallel_pread": (_int, [C.c_char_p, _i64, _i64, _vp]),
+    "pg_preprocess_stlfr": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _i64, _P(_i64), _vp, _i64, _P(_i64)]),
+    "pg_preprocess_tellseq": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _P(_i64), _vp, _i64, _P(_i64), _vp, _i64, _P(_i64)]),
+    "pg_extract_open": (_int, [_vp, _vp, _i64, _P(_vp)]),
+    "pg_extract_n_runs": (_i64, [_vp]),
+    "pg_extract_run_labels": (_i64, [_vp, _vp, _i64, _vp]),
+    "pg_extract_route": (_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "pg_extract_copy": (_int, [_vp, _vp, _vp, _vp]),
+    "pg_extract_close": (None, [_vp, _vp]),
     "pg_sampler_create": (_int, [_vp, _vp, _i64, C.c_double, _P(_vp)]),
     "pg_sampler_free": (None, [_vp, _vp]),
     "pg_sampler_draw": (_int, [_vp, _vp, _vp, _i64, _vp]),

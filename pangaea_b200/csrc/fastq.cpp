@@ -755,6 +755,32 @@ extern "C" int pg_parallel_memcpy(void* dst, const void* src, int64_t n)
     } catch (...) { return PG_ERR_IO; }
 }
 
+// file bytes [offset, offset + n) -> dst with all host cores, each thread pread()ing its slice: one kernel copy from the page
+// cache (or the disk) straight into the caller's - pinned - buffer, no page faults on a mapping
+extern "C" int pg_parallel_pread(const char* path, int64_t offset, int64_t n, void* dst)
+{
+    if (!path || offset < 0 || n < 0 || (n && !dst)) return PG_ERR_INVALID;
+    if (n == 0) return PG_OK;
+    try {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return PG_ERR_IO;
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(parallel_threads(), n / (4 << 20) + 1));
+        std::vector<int> ok((size_t)T, 1);
+        run_threads(T, [&](int t) {
+            int64_t lo = n / T * t;
+            const int64_t hi = t + 1 == T ? n : n / T * (t + 1);
+            while (lo < hi) {
+                const ssize_t got = ::pread(fd, (char*)dst + lo, (size_t)std::min<int64_t>(hi - lo, 1 << 30), (off_t)(offset + lo));
+                if (got <= 0) { ok[(size_t)t] = 0; return; }
+                lo += got;
+            }
+        });
+        ::close(fd);
+        for (int v : ok) if (!v) return PG_ERR_IO;
+        return PG_OK;
+    } catch (...) { return PG_ERR_IO; }
+}
+
 extern "C" int pg_fastq_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int64_t* n_newlines)
 {
     if (!path || !n_newlines || byte_lo < 0) return PG_ERR_INVALID;

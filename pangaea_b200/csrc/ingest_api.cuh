@@ -494,3 +494,315 @@ extern "C" int pg_features_gather(pg_ctx* ctx, const pg_features* f, const int64
     if (*(const uint32_t*)ctx->h_pin) return fail(ctx, PG_ERR_INVALID, "pg_features_gather: row index out of range");
     return PG_OK;
 }
+
+// ---------------------------------------------------------------------------
+// format converters and extract_reads (transform.cuh)
+// ---------------------------------------------------------------------------
+#include "transform.cuh"
+
+namespace {
+struct DevText { // a host text uploaded with its line index
+    uint8_t* text = nullptr;
+    long long* line_start = nullptr;
+    int64_t n = 0, n_lines = 0;
+    TextLines lines() const { return TextLines{ text, line_start, n_lines }; }
+};
+} // namespace
+
+static int dev_text_upload(pg_ctx* ctx, const char* host, int64_t n, DevText* t)
+{
+    t->n = n;
+    CK(dmalloc(ctx, &t->text, (size_t)n + 64));
+    if (n) CK(cudaMemcpyAsync(t->text, host, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return build_line_index(ctx, t->text, n, &t->line_start, &t->n_lines);
+}
+static void dev_text_free(pg_ctx* ctx, DevText* t) { dfree(ctx, t->text); dfree(ctx, t->line_start); *t = DevText(); }
+
+// scan lengths -> offsets, fetch the total
+static int offsets_of(pg_ctx* ctx, const long long* len, int64_t n, long long* off, int64_t* total)
+{
+    int rc = scan64(ctx, len, n, off, (long long*)ctx->d_scalar);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total = ctx->h_pin[0];
+    return PG_OK;
+}
+
+extern "C" int pg_preprocess_stlfr(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, int library, char* out1, int64_t cap1,
+                                   int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2)
+{
+    if (!ctx || n1 < 0 || n2 < 0 || (n1 && !r1) || (n2 && !r2) || !n_out1 || !n_out2) return fail(ctx, PG_ERR_INVALID, "pg_preprocess_stlfr: bad argument");
+    *n_out1 = *n_out2 = 0;
+    CK(cudaSetDevice(ctx->p.device));
+    DevText A, B;
+    long long *len1 = nullptr, *len2 = nullptr, *off1 = nullptr, *off2 = nullptr;
+    uint8_t *o1 = nullptr, *o2 = nullptr;
+    uint32_t* bad = nullptr;
+    auto done = [&](int rc) {
+        dev_text_free(ctx, &A); dev_text_free(ctx, &B);
+        dfree(ctx, len1); dfree(ctx, len2); dfree(ctx, off1); dfree(ctx, off2); dfree(ctx, o1); dfree(ctx, o2); dfree(ctx, bad);
+        return rc;
+    };
+    int rc = dev_text_upload(ctx, r1, n1, &A);
+    if (!rc) rc = dev_text_upload(ctx, r2, n2, &B);
+    if (rc) return done(rc);
+    const int64_t nl = A.n_lines;
+    if (nl == 0) return done(PG_OK);
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    CKT(dmalloc(ctx, &len1, (size_t)nl)); CKT(dmalloc(ctx, &len2, (size_t)nl)); CKT(dmalloc(ctx, &off1, (size_t)nl)); CKT(dmalloc(ctx, &off2, (size_t)nl));
+    CKT(dmalloc(ctx, &bad, 1));
+    CKT(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    stlfr_size_kernel<<<(int)((nl + 255) / 256), 256, 0, ctx->stream>>>(A.lines(), B.lines(), library, len1, len2, bad);
+    CKT(cudaGetLastError());
+    int64_t t1 = 0, t2 = 0;
+    rc = offsets_of(ctx, len1, nl, off1, &t1);
+    if (!rc) rc = offsets_of(ctx, len2, nl, off2, &t2);
+    if (rc) return done(rc);
+    uint32_t h_bad = 0;
+    CKT(cudaMemcpy(&h_bad, bad, sizeof(h_bad), cudaMemcpyDeviceToHost));
+    if (h_bad) return done(fail(ctx, PG_ERR_INVALID, "pg_preprocess_stlfr: a header without '#' or a barcode that is not a_b_c (the reference tool aborts on it)"));
+    *n_out1 = t1; *n_out2 = t2;
+    if (t1 > cap1 || t2 > cap2 || !out1 || !out2) return done(fail(ctx, PG_ERR_INVALID, "pg_preprocess_stlfr: output buffers too small (sizes are in n_out1 / n_out2)"));
+    CKT(dmalloc(ctx, &o1, (size_t)t1 + 64)); CKT(dmalloc(ctx, &o2, (size_t)t2 + 64));
+    stlfr_write_kernel<<<(int)((nl * 64 + 255) / 256), 256, 0, ctx->stream>>>(A.lines(), B.lines(), library, off1, off2, o1, o2);
+    CKT(cudaGetLastError());
+    CKT(cudaMemcpyAsync(out1, o1, (size_t)t1, cudaMemcpyDeviceToHost, ctx->stream));
+    CKT(cudaMemcpyAsync(out2, o2, (size_t)t2, cudaMemcpyDeviceToHost, ctx->stream));
+    CKT(cudaStreamSynchronize(ctx->stream));
+    return done(PG_OK);
+}
+
+extern "C" int pg_preprocess_tellseq(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, const char* idx, int64_t ni, char* out1,
+                                     int64_t cap1, int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2, char* out_wl, int64_t cap_wl,
+                                     int64_t* n_out_wl)
+{
+    if (!ctx || n1 < 0 || n2 < 0 || ni < 0 || (n1 && !r1) || (n2 && !r2) || (ni && !idx) || !n_out1 || !n_out2 || !n_out_wl)
+        return fail(ctx, PG_ERR_INVALID, "pg_preprocess_tellseq: bad argument");
+    *n_out1 = *n_out2 = *n_out_wl = 0;
+    CK(cudaSetDevice(ctx->p.device));
+    DevText A, B, I;
+    long long *len1 = nullptr, *len2 = nullptr, *lenw = nullptr, *off1 = nullptr, *off2 = nullptr, *offw = nullptr;
+    uint8_t *o1 = nullptr, *o2 = nullptr, *ow = nullptr;
+    auto done = [&](int rc) {
+        dev_text_free(ctx, &A); dev_text_free(ctx, &B); dev_text_free(ctx, &I);
+        dfree(ctx, len1); dfree(ctx, len2); dfree(ctx, lenw); dfree(ctx, off1); dfree(ctx, off2); dfree(ctx, offw); dfree(ctx, o1); dfree(ctx, o2); dfree(ctx, ow);
+        return rc;
+    };
+    int rc = dev_text_upload(ctx, r1, n1, &A);
+    if (!rc) rc = dev_text_upload(ctx, r2, n2, &B);
+    if (!rc) rc = dev_text_upload(ctx, idx, ni, &I);
+    if (rc) return done(rc);
+    const int64_t n_rec = A.n_lines / 4; // a record is written when its fourth line has been read
+    if (n_rec == 0) return done(PG_OK);
+    CKT(dmalloc(ctx, &len1, (size_t)n_rec)); CKT(dmalloc(ctx, &len2, (size_t)n_rec)); CKT(dmalloc(ctx, &lenw, (size_t)n_rec));
+    CKT(dmalloc(ctx, &off1, (size_t)n_rec)); CKT(dmalloc(ctx, &off2, (size_t)n_rec)); CKT(dmalloc(ctx, &offw, (size_t)n_rec));
+    tellseq_size_kernel<<<(int)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(A.lines(), B.lines(), I.lines(), n_rec, len1, len2, lenw);
+    CKT(cudaGetLastError());
+    int64_t t1 = 0, t2 = 0, tw = 0;
+    rc = offsets_of(ctx, len1, n_rec, off1, &t1);
+    if (!rc) rc = offsets_of(ctx, len2, n_rec, off2, &t2);
+    if (!rc) rc = offsets_of(ctx, lenw, n_rec, offw, &tw);
+    if (rc) return done(rc);
+    *n_out1 = t1; *n_out2 = t2; *n_out_wl = tw;
+    if (t1 > cap1 || t2 > cap2 || tw > cap_wl || (t1 && !out1) || (t2 && !out2) || (tw && !out_wl))
+        return done(fail(ctx, PG_ERR_INVALID, "pg_preprocess_tellseq: output buffers too small (sizes are in n_out*)"));
+    CKT(dmalloc(ctx, &o1, (size_t)t1 + 64)); CKT(dmalloc(ctx, &o2, (size_t)t2 + 64)); CKT(dmalloc(ctx, &ow, (size_t)tw + 64));
+    tellseq_write_kernel<<<(int)((n_rec * 64 + 255) / 256), 256, 0, ctx->stream>>>(A.lines(), B.lines(), I.lines(), n_rec, len1, off1, off2, offw, o1, o2, ow);
+    CKT(cudaGetLastError());
+    if (t1) CKT(cudaMemcpyAsync(out1, o1, (size_t)t1, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t2) CKT(cudaMemcpyAsync(out2, o2, (size_t)t2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tw) CKT(cudaMemcpyAsync(out_wl, ow, (size_t)tw, cudaMemcpyDeviceToHost, ctx->stream));
+    CKT(cudaStreamSynchronize(ctx->stream));
+    return done(PG_OK);
+}
+
+// ---- extract_reads -i -------------------------------------------------------
+struct pg_extract {
+    DevText T;
+    int64_t n_rec = 0;
+    unsigned long long latch = ~0ull;
+    long long *bc_off = nullptr, *change = nullptr, *run_of_rec = nullptr;
+    int32_t* bc_len = nullptr;
+    std::vector<std::string> run_labels; // run 0 = records whose barcode equals "" from the start of the file
+    // after pg_extract_route
+    uint8_t *out_fq = nullptr, *out_bc = nullptr;
+    int64_t fq_total = 0, bc_total = 0;
+};
+
+extern "C" void pg_extract_close(pg_ctx* ctx, pg_extract* x)
+{
+    if (!x) return;
+    if (ctx) {
+        cudaSetDevice(ctx->p.device);
+        dev_text_free(ctx, &x->T);
+        dfree(ctx, x->bc_off); dfree(ctx, x->change); dfree(ctx, x->run_of_rec); dfree(ctx, x->bc_len); dfree(ctx, x->out_fq); dfree(ctx, x->out_bc);
+    }
+    delete x;
+}
+
+extern "C" int pg_extract_open(pg_ctx* ctx, const char* text, int64_t n_bytes, pg_extract** out)
+{
+    if (!ctx || !out || n_bytes < 0 || (n_bytes && !text)) return fail(ctx, PG_ERR_INVALID, "pg_extract_open: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->p.device));
+    pg_extract* x = new pg_extract();
+    x->run_labels.emplace_back("");
+    auto bail = [&](int rc) { pg_extract_close(ctx, x); return rc; };
+    int rc = dev_text_upload(ctx, text, n_bytes, &x->T);
+    if (rc) return bail(rc);
+    const int64_t n_rec = (x->T.n_lines + 7) / 8;
+    x->n_rec = n_rec;
+    if (n_rec == 0) { *out = x; return PG_OK; }
+#define CKX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    TextLines T = x->T.lines();
+    unsigned long long* d_latch = (unsigned long long*)ctx->d_scalar;
+    CKX(cudaMemsetAsync(d_latch, 0xFF, sizeof(unsigned long long), ctx->stream));
+    const int g = (int)((n_rec + 255) / 256);
+    latch_kernel<<<g, 256, 0, ctx->stream>>>(T, 8, n_rec, d_latch);
+    CKX(cudaMemcpyAsync(ctx->h_pin, d_latch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CKX(cudaStreamSynchronize(ctx->stream));
+    x->latch = (unsigned long long)ctx->h_pin[0];
+    long long *read_bytes = nullptr, *change_excl = nullptr;
+    uint8_t* flag2 = nullptr;
+    CKX(dmalloc(ctx, &x->bc_off, (size_t)n_rec)); CKX(dmalloc(ctx, &x->bc_len, (size_t)n_rec)); CKX(dmalloc(ctx, &x->change, (size_t)n_rec));
+    CKX(dmalloc(ctx, &x->run_of_rec, (size_t)n_rec));
+    CKX(dmalloc(ctx, &read_bytes, (size_t)2 * n_rec)); CKX(dmalloc(ctx, &flag2, (size_t)2 * n_rec)); CKX(dmalloc(ctx, &change_excl, (size_t)n_rec));
+    barcode_kernel<<<g, 256, 0, ctx->stream>>>(T, n_rec, x->latch, x->bc_off, x->bc_len);
+    // barcode runs: a record starts a new run when its barcode differs from the record before (record 0: from "");
+    // reads_kernel's change flag needs line 8r + 5 to exist, which holds for every record that extract_reads can output
+    reads_kernel<<<g, 256, 0, ctx->stream>>>(T, n_rec, x->bc_off, x->bc_len, nullptr, 0, read_bytes, flag2, x->change);
+    CKX(cudaGetLastError());
+    rc = scan64(ctx, x->change, n_rec, change_excl, (long long*)ctx->d_scalar);
+    if (rc) { dfree(ctx, read_bytes); dfree(ctx, flag2); dfree(ctx, change_excl); return bail(rc); }
+    run_index_kernel<<<g, 256, 0, ctx->stream>>>(x->change, change_excl, n_rec, x->run_of_rec);
+    CKX(cudaMemcpyAsync(ctx->h_pin, ctx->d_scalar, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CKX(cudaStreamSynchronize(ctx->stream));
+    const int64_t n_lab = ctx->h_pin[0];
+    if (n_lab) { // labels of the runs, as pg_ingest_text collects the labels of the clouds
+        long long *lab_off = nullptr, *lab_len = nullptr, *lab_start = nullptr;
+        uint8_t* blob = nullptr;
+        CKX(dmalloc(ctx, &lab_off, (size_t)n_lab)); CKX(dmalloc(ctx, &lab_len, (size_t)n_lab)); CKX(dmalloc(ctx, &lab_start, (size_t)n_lab));
+        label_spans_kernel<<<g, 256, 0, ctx->stream>>>(n_rec, x->change, change_excl, x->bc_off, x->bc_len, lab_off, lab_len);
+        int64_t blob_bytes = 0;
+        rc = offsets_of(ctx, lab_len, n_lab, lab_start, &blob_bytes);
+        if (!rc) {
+            CKX(dmalloc(ctx, &blob, (size_t)blob_bytes + 1));
+            label_copy_kernel<<<(int)((n_lab + 255) / 256), 256, 0, ctx->stream>>>(x->T.text, n_lab, lab_off, lab_len, lab_start, blob);
+            std::vector<char> h_blob((size_t)blob_bytes + 1);
+            std::vector<long long> h_start((size_t)n_lab), h_len((size_t)n_lab);
+            CKX(cudaMemcpyAsync(h_blob.data(), blob, (size_t)blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CKX(cudaMemcpyAsync(h_start.data(), lab_start, (size_t)n_lab * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CKX(cudaMemcpyAsync(h_len.data(), lab_len, (size_t)n_lab * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CKX(cudaStreamSynchronize(ctx->stream));
+            for (int64_t k = 0; k < n_lab; ++k) x->run_labels.emplace_back(h_blob.data() + h_start[(size_t)k], (size_t)h_len[(size_t)k]);
+        }
+        dfree(ctx, lab_off); dfree(ctx, lab_len); dfree(ctx, lab_start); dfree(ctx, blob);
+    }
+    dfree(ctx, read_bytes); dfree(ctx, flag2); dfree(ctx, change_excl);
+    if (rc) return bail(rc);
+    *out = x;
+    return PG_OK;
+}
+
+extern "C" int64_t pg_extract_n_runs(const pg_extract* x) { return x ? (int64_t)x->run_labels.size() : -1; }
+extern "C" int64_t pg_extract_run_labels(const pg_extract* x, char* buf, int64_t cap, int64_t* offsets)
+{
+    if (!x) return -1;
+    int64_t need = 0;
+    for (auto& l : x->run_labels) need += (int64_t)l.size();
+    if (!buf || !offsets || cap < need) return need;
+    int64_t at = 0;
+    size_t i = 0;
+    for (auto& l : x->run_labels) { offsets[i++] = at; memcpy(buf + at, l.data(), l.size()); at += (int64_t)l.size(); }
+    offsets[i] = at;
+    return need;
+}
+
+// cluster_of_run[n_runs]: cluster index (0 .. n_clusters - 1) or -1.  fq_start / bc_start: n_clusters + 1 byte offsets of every
+// cluster's slice in the two output blobs (pg_extract_copy)
+extern "C" int pg_extract_route(pg_ctx* ctx, pg_extract* x, const int32_t* cluster_of_run, int32_t n_clusters, int64_t* fq_start, int64_t* bc_start)
+{
+    if (!ctx || !x || !cluster_of_run || n_clusters < 0 || n_clusters > 65000 || !fq_start || !bc_start) return fail(ctx, PG_ERR_INVALID, "pg_extract_route: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    for (int c = 0; c <= n_clusters; ++c) fq_start[c] = bc_start[c] = 0;
+    const int64_t n_rec = x->n_rec;
+    if (n_rec == 0) return PG_OK;
+    const int64_t n_runs = (int64_t)x->run_labels.size();
+    std::vector<void*> tmp;
+    auto done = [&](int rc) { for (void* p : tmp) dfree(ctx, p); return rc; };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+    int32_t* d_cl = nullptr;
+    long long *fq_len = nullptr, *bc_out_len = nullptr, *fq_sorted = nullptr, *bc_sorted = nullptr, *fq_off = nullptr, *bc_off2 = nullptr, *hist = nullptr;
+    uint8_t *key_lo = nullptr, *key_hi = nullptr;
+    uint32_t *perm_a = nullptr, *perm_b = nullptr;
+    CKR(dmalloc(ctx, &d_cl, (size_t)n_runs)); tmp.push_back(d_cl);
+    CKR(dmalloc(ctx, &fq_len, (size_t)n_rec)); tmp.push_back(fq_len);
+    CKR(dmalloc(ctx, &bc_out_len, (size_t)n_rec)); tmp.push_back(bc_out_len);
+    CKR(dmalloc(ctx, &fq_sorted, (size_t)n_rec)); tmp.push_back(fq_sorted);
+    CKR(dmalloc(ctx, &bc_sorted, (size_t)n_rec)); tmp.push_back(bc_sorted);
+    CKR(dmalloc(ctx, &fq_off, (size_t)n_rec)); tmp.push_back(fq_off);
+    CKR(dmalloc(ctx, &bc_off2, (size_t)n_rec)); tmp.push_back(bc_off2);
+    CKR(dmalloc(ctx, &key_lo, (size_t)n_rec)); tmp.push_back(key_lo);
+    CKR(dmalloc(ctx, &key_hi, (size_t)n_rec)); tmp.push_back(key_hi);
+    CKR(dmalloc(ctx, &perm_a, (size_t)n_rec)); tmp.push_back(perm_a);
+    CKR(dmalloc(ctx, &perm_b, (size_t)n_rec)); tmp.push_back(perm_b);
+    CKR(cudaMemcpyAsync(d_cl, cluster_of_run, (size_t)n_runs * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    TextLines T = x->T.lines();
+    const int g = (int)((n_rec + 255) / 256);
+    extract_size_kernel<<<g, 256, 0, ctx->stream>>>(T, n_rec, x->latch, x->run_of_rec, d_cl, x->bc_len, fq_len, bc_out_len, key_lo, key_hi);
+    iota_kernel<<<g, 256, 0, ctx->stream>>>(perm_a, n_rec);
+    CKR(cudaGetLastError());
+    // stable sort of the records by cluster (two 8-bit radix passes): file order is kept inside every cluster
+    const int64_t n_chunks = (n_rec + kRadixChunk - 1) / kRadixChunk;
+    CKR(dmalloc(ctx, &hist, (size_t)256 * n_chunks)); tmp.push_back(hist);
+    const int g_radix = (int)((n_chunks + kRadixWarps - 1) / kRadixWarps);
+    for (const uint8_t* col : { (const uint8_t*)key_lo, (const uint8_t*)key_hi }) {
+        radix_hist_kernel<<<g_radix, kRadixWarps * 32, 0, ctx->stream>>>(col, perm_a, n_rec, n_chunks, hist);
+        int rc = scan64(ctx, hist, 256 * n_chunks, hist, nullptr);
+        if (rc) return done(rc);
+        radix_scatter_kernel<<<g_radix, kRadixWarps * 32, 0, ctx->stream>>>(col, perm_a, n_rec, n_chunks, hist, perm_b);
+        std::swap(perm_a, perm_b);
+    }
+    gather_len_kernel<<<g, 256, 0, ctx->stream>>>(fq_len, perm_a, n_rec, fq_sorted);
+    gather_len_kernel<<<g, 256, 0, ctx->stream>>>(bc_out_len, perm_a, n_rec, bc_sorted);
+    CKR(cudaGetLastError());
+    int rc = offsets_of(ctx, fq_sorted, n_rec, fq_off, &x->fq_total);
+    if (!rc) rc = offsets_of(ctx, bc_sorted, n_rec, bc_off2, &x->bc_total);
+    if (rc) return done(rc);
+    // per-cluster slices: bytes of cluster c = sum of its records' lengths (host side: the per-record arrays are small next to the text)
+    {
+        std::vector<long long> h_len((size_t)n_rec), h_bcl((size_t)n_rec);
+        std::vector<uint8_t> h_lo((size_t)n_rec), h_hi((size_t)n_rec);
+        CKR(cudaMemcpy(h_len.data(), fq_len, (size_t)n_rec * 8, cudaMemcpyDeviceToHost));
+        CKR(cudaMemcpy(h_bcl.data(), bc_out_len, (size_t)n_rec * 8, cudaMemcpyDeviceToHost));
+        CKR(cudaMemcpy(h_lo.data(), key_lo, (size_t)n_rec, cudaMemcpyDeviceToHost));
+        CKR(cudaMemcpy(h_hi.data(), key_hi, (size_t)n_rec, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> fq_sz((size_t)n_clusters + 1, 0), bc_sz((size_t)n_clusters + 1, 0);
+        for (int64_t r = 0; r < n_rec; ++r) {
+            const int c = h_lo[(size_t)r] | (h_hi[(size_t)r] << 8);
+            if (c < n_clusters) { fq_sz[(size_t)c] += h_len[(size_t)r]; bc_sz[(size_t)c] += h_bcl[(size_t)r]; }
+        }
+        int64_t a = 0, b = 0;
+        for (int c = 0; c < n_clusters; ++c) { fq_start[c] = a; bc_start[c] = b; a += fq_sz[(size_t)c]; b += bc_sz[(size_t)c]; }
+        fq_start[n_clusters] = a; bc_start[n_clusters] = b;
+    }
+    dfree(ctx, x->out_fq); dfree(ctx, x->out_bc);
+    x->out_fq = x->out_bc = nullptr;
+    CKR(dmalloc(ctx, &x->out_fq, (size_t)x->fq_total + 64));
+    CKR(dmalloc(ctx, &x->out_bc, (size_t)x->bc_total + 64));
+    extract_write_kernel<<<(int)((n_rec * 32 + 255) / 256), 256, 0, ctx->stream>>>(T, n_rec, x->latch, perm_a, fq_sorted, fq_off, bc_off2, x->out_fq, x->out_bc);
+    CKR(cudaGetLastError());
+    CKR(cudaStreamSynchronize(ctx->stream));
+    return done(PG_OK);
+}
+
+extern "C" int pg_extract_copy(pg_ctx* ctx, const pg_extract* x, char* fq_out, char* bc_out)
+{
+    if (!ctx || !x) return fail(ctx, PG_ERR_INVALID, "pg_extract_copy: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    if (x->fq_total && fq_out) CK(cudaMemcpyAsync(fq_out, x->out_fq, (size_t)x->fq_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (x->bc_total && bc_out) CK(cudaMemcpyAsync(bc_out, x->out_bc, (size_t)x->bc_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}

@@ -72,7 +72,6 @@ class DeviceIngest:
             batch, labels, keep, _, _ = ctx.ingest_text(b"", b"", 0, final=True)
             yield batch, keep, labels, True
             return
-        mm = np.memmap(self.path, dtype=np.uint8, mode="r")
         L = _lib.lib()
         window, slack = self.window, self.slack
         state = {}
@@ -81,9 +80,11 @@ class DeviceIngest:
             state["bufs"] = [torch.empty(slack + window, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
             state["views"] = [b.numpy() for b in state["bufs"]]
 
-        def stage(k, lo, hi):  # file bytes [lo, hi) -> views[k][slack : slack + hi - lo], all cores
-            if hi > lo:
-                L.pg_parallel_memcpy(state["views"][k][slack:].ctypes.data, mm[lo:hi].ctypes.data, hi - lo)
+        fs_path = _lib.os.fsencode(self.path)
+
+        def stage(k, lo, hi):  # file bytes [lo, hi) -> views[k][slack : slack + hi - lo]: pread on all cores, no mapping
+            if hi > lo and L.pg_parallel_pread(fs_path, lo, hi - lo, state["views"][k][slack:].ctypes.data) != 0:
+                state["error"] = _lib.PgError(-4, f"cannot read {self.path!r}")  # (may run on the staging thread)
 
         alloc()
         last, rt = b"", 0
@@ -100,6 +101,8 @@ class DeviceIngest:
             batch, labels, keep, consumed, rt = ctx.ingest_text(chunk, last, rt, final=final, n_bytes=len(chunk))
             if nxt:
                 nxt.join()
+            if "error" in state:
+                raise state["error"]
             restart = None
             if batch is None:               # no cloud flush inside the chunk (a cloud larger than the window): take a larger one
                 if final:
