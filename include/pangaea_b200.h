@@ -152,6 +152,10 @@ int pg_table_clamp(pg_ctx* ctx, uint32_t max_count);
  * (countKmer, count_tnf.cpp:78-113) in one pass over the packed bases.  group_keep:
  * n_groups bytes (host memory), see header comment.  Rows come out in file order. */
 int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out);
+/* flags = PG_FEAT_NO_ABUNDANCE: cloud grouping, rows and TNF only; the abundance matrix stays zero for pg_features_add_counts
+ * (the owner-partitioned multi-GPU table, below: the counts come from other ranks) */
+enum { PG_FEAT_NO_ABUNDANCE = 1 };
+int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, int flags, pg_features** out);
 void pg_features_free(pg_ctx* ctx, pg_features* f);
 int64_t pg_features_rows(const pg_features* f);
 int32_t pg_features_abd_dim(const pg_features* f);
@@ -160,6 +164,20 @@ int32_t pg_features_tnf_dim(const pg_features* f);
 int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t* groups_out);
 /* raw tallies, int32 row-major [rows, dim] - what the CSV files held as text */
 int pg_features_copy_raw(pg_ctx* ctx, const pg_features* f, int32_t* abd_out, int32_t* tnf_out);
+
+/* ---- owner-partitioned table across ranks (owner = hash(canonical k-mer) mod n_ranks) ------------------
+ * The multi-GPU form of the HASH table (k > 16), which has no dense view to all-reduce.  Device side of the two all-to-alls;
+ * the collective itself belongs to the caller (torch.distributed / NCCL - pangaea_b200/distributed.py):
+ *   count     keys = pg_batch_window_keys(count windows) -> pg_keys_partition -> all-to-all of keys -> pg_table_add_keys
+ *   featurize f = pg_featurize2(NO_ABUNDANCE); keys(feature windows) -> pg_keys_partition -> all-to-all of keys ->
+ *             pg_table_lookup_keys at the owner -> all-to-all of counts back -> pg_features_add_counts
+ * All d_* arguments are device memory.  Keys are the canonical forms of the reference (count_kmer.cpp:86), ~0 = no window. */
+int64_t pg_batch_n_words(const pg_batch* b);
+int pg_batch_window_keys(pg_ctx* ctx, pg_batch* b, int64_t w0, int64_t w1, int feature_windows, uint64_t* d_keys /* 32 x (w1 - w0) */);
+int pg_keys_partition(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, int32_t world, uint64_t* d_sorted, int64_t* d_dest, int64_t* counts_out);
+int pg_table_add_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n);
+int pg_table_lookup_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, uint32_t* d_counts);
+int pg_features_add_counts(pg_ctx* ctx, pg_features* f, pg_batch* b, int64_t w0, int64_t w1, const int64_t* d_dest, const uint32_t* d_counts_sorted);
 
 /* ---- step 2 prologue: Data.__init__ (src/data.py:16-21) --------------------- */
 /* L1-normalise both matrices (fp64 divide, fp32 store) and weights = max(abd row)^2 (fp64).  The reference normalises

@@ -74,6 +74,13 @@ SIGNATURES = {
     "pg_table_wait_event": (_int, [_vp, _vp]),
     "pg_table_clamp": (_int, [_vp, C.c_uint32]),
     "pg_featurize": (_int, [_vp, _vp, _vp, _i64, _P(_vp)]),
+    "pg_featurize2": (_int, [_vp, _vp, _vp, _i64, _int, _P(_vp)]),
+    "pg_batch_n_words": (_i64, [_vp]),
+    "pg_batch_window_keys": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
+    "pg_keys_partition": (_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "pg_table_add_keys": (_int, [_vp, _vp, _i64]),
+    "pg_table_lookup_keys": (_int, [_vp, _vp, _i64, _vp]),
+    "pg_features_add_counts": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "pg_features_free": (None, [_vp, _vp]),
     "pg_features_rows": (_i64, [_vp]),
     "pg_features_abd_dim": (_i32, [_vp]),
@@ -496,12 +503,12 @@ class Context:
         return torch.as_tensor(_Arr(), device=f"cuda:{self.params.device}")
 
     # ---- features ------------------------------------------------------------
-    def featurize(self, batch: Batch, group_keep, n_groups=None) -> Features:
+    def featurize(self, batch: Batch, group_keep, n_groups=None, no_abundance=False) -> Features:
         if isinstance(group_keep, np.ndarray):
             group_keep = np.ascontiguousarray(group_keep, dtype=np.uint8)
             n_groups = len(group_keep) if n_groups is None else n_groups
         h = _vp()
-        self._ck(lib().pg_featurize(self.h, batch.h, _ptr(group_keep), int(n_groups), C.byref(h)))
+        self._ck(lib().pg_featurize2(self.h, batch.h, _ptr(group_keep), int(n_groups), 1 if no_abundance else 0, C.byref(h)))
         return Features(self, h)
 
     def extract_features(self, reads: pg_reads, group_keep, n_groups=None) -> Features:

@@ -17,6 +17,7 @@
 #include "bucket.cuh"
 #include "count.cuh"
 #include "count2.cuh"
+#include "exchange.cuh"
 #include "featurize.cuh"
 #include "kmer.cuh"
 #include "normalize.cuh"
@@ -131,6 +132,8 @@ struct pg_features {
     float *abd = nullptr, *tnf = nullptr;
     double* weights = nullptr;
     int32_t* group_of_row = nullptr;
+    int32_t* row_of_group = nullptr; // kept only by pg_featurize2(PG_FEAT_NO_ABUNDANCE): pg_features_add_counts maps cloud -> row with it
+    int64_t n_groups = 0;
     bool normalized = false;
 };
 
@@ -1163,9 +1166,15 @@ static int group_stage_a(pg_ctx* ctx, pg_batch* b, bool want_wg, bool packed)
 
 extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
 {
+    return pg_featurize2(ctx, b, group_keep, n_groups, 0, out);
+}
+
+extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, int flags, pg_features** out)
+{
     if (!ctx || !b || !out || n_groups < 1 || !group_keep) return fail(ctx, PG_ERR_INVALID, "pg_featurize: bad argument");
     *out = nullptr;
-    if (!ctx->counted || !ctx->have_table()) return fail(ctx, PG_ERR_STATE, "pg_featurize: the k-mer table is empty - call pg_count / pg_table_set first");
+    const bool no_abd = (flags & PG_FEAT_NO_ABUNDANCE) != 0;
+    if (!no_abd && (!ctx->counted || !ctx->have_table())) return fail(ctx, PG_ERR_STATE, "pg_featurize: the k-mer table is empty - call pg_count / pg_table_set first");
     if (n_groups > 0x7FFFFFFFll) return fail(ctx, PG_ERR_INVALID, "more than 2^31 clouds in one batch");
     CK(cudaSetDevice(ctx->p.device));
 
@@ -1174,7 +1183,7 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
     int64_t rows = 0;
     int rc = PG_OK;
     pg_features* f = nullptr;
-    const bool sliced = use_buckets(ctx);
+    const bool sliced = use_buckets(ctx) || no_abd; // (no_abd: grouping + the TNF kernel of the sliced path, no look-ups at all)
     cudaEvent_t tnf_fork = nullptr, tnf_join = nullptr; // TNF kernel on the second stream (sliced path)
     auto cleanup = [&]() {
         if (tnf_join) { cudaStreamWaitEvent(ctx->stream, tnf_join, 0); ctx->pool.push_back(tnf_fork); ctx->pool.push_back(tnf_join); tnf_fork = tnf_join = nullptr; }
@@ -1280,6 +1289,14 @@ extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep,
                 }
                 if (side) CKF(cudaEventRecord(tnf_join, ts));
             }
+            if (no_abd) { // the caller adds the abundance tallies itself (pg_features_add_counts): it needs cloud -> row
+                f->row_of_group = row_of_group; f->n_groups = n_groups;
+                row_of_group = nullptr;
+                CKF(cudaGetLastError());
+                cleanup();
+                *out = f;
+                return PG_OK;
+            }
             rc = table_ready(ctx); // the table may still be inside an all-reduce: grouping and TNF above did not need it
             if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
             // entries kept by pg_count (shared partition)?  usable unless an overflow path bypassed the buffer
@@ -1362,7 +1379,7 @@ static void features_release(pg_features* f, pg_ctx* ctx = nullptr)
 {
     if (f->refs.fetch_sub(1) > 1) return;
     cudaSetDevice(f->device);
-    void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
+    void* bufs[7] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row, f->row_of_group };
     for (void* p : bufs) {
         if (!p) continue;
         if (ctx) dfree(ctx, p); else cudaFree(p);
@@ -1490,7 +1507,7 @@ extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
     cudaStreamSynchronize(ctx->stream); // the consumer runs on its own stream
     {   // the consumer's deleter may run on any thread, after the ctx is gone: take the buffers out of the ctx's block
         // cache - from here on they are plain cudaMalloc blocks, released with cudaFree / cudaFreeAsync
-        void* bufs[6] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row };
+        void* bufs[7] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row, f->row_of_group };
         for (void* p : bufs) if (p) ctx->big.live.erase(p);
     }
     DlHolder* h = new DlHolder();

@@ -806,3 +806,101 @@ extern "C" int pg_extract_copy(pg_ctx* ctx, const pg_extract* x, char* fq_out, c
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// owner-partitioned table across ranks (exchange.cuh): the device side of the two all-to-alls
+// ---------------------------------------------------------------------------
+extern "C" int64_t pg_batch_n_words(const pg_batch* b) { return b ? b->n_words : -1; }
+
+extern "C" int pg_batch_window_keys(pg_ctx* ctx, pg_batch* b, int64_t w0, int64_t w1, int feature_windows, uint64_t* d_keys)
+{
+    if (!ctx || !b || w0 < 0 || w1 < w0 || w1 > b->n_words || (w1 > w0 && !d_keys)) return fail(ctx, PG_ERR_INVALID, "pg_batch_window_keys: bad argument");
+    if (w1 == w0) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    if (feature_windows && !b->grouped) return fail(ctx, PG_ERR_STATE, "pg_batch_window_keys: call pg_featurize2 first (it derives the feature mask)");
+    const uint32_t* mask = feature_windows ? (b->maskR ? b->maskR : b->maskF) : b->maskC;
+    window_keys_kernel<<<(int)((w1 - w0 + 255) / 256), 256, 0, ctx->stream>>>(b->codes, mask, w0, w1, ctx->p.k, (unsigned long long*)d_keys);
+    CK(cudaGetLastError());
+    return PG_OK;
+}
+
+// d_sorted: the keys grouped by owner (owner 0 first); d_dest[i] = position of key i in d_sorted or -1; counts_out[world] on the host
+extern "C" int pg_keys_partition(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, int32_t world, uint64_t* d_sorted, int64_t* d_dest, int64_t* counts_out)
+{
+    if (!ctx || n < 0 || world < 1 || world > 64 || !counts_out || (n && (!d_keys || !d_sorted || !d_dest))) return fail(ctx, PG_ERR_INVALID, "pg_keys_partition: bad argument");
+    for (int r = 0; r < world; ++r) counts_out[r] = 0;
+    if (!n) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    unsigned long long* d_cnt = nullptr;
+    CK(dmalloc(ctx, &d_cnt, 64));
+    CK(cudaMemsetAsync(d_cnt, 0, 64 * sizeof(unsigned long long), ctx->stream));
+    const int grid = grid_for(n, 256, ctx->sm_count * 8);
+    owner_count_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned long long*)d_keys, n, (uint32_t)world, d_cnt);
+    unsigned long long h_cnt[64];
+    CK(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h_start[64], acc = 0;
+    for (int r = 0; r < world; ++r) { counts_out[r] = (int64_t)h_cnt[r]; h_start[r] = acc; acc += h_cnt[r]; }
+    CK(cudaMemcpyAsync(d_cnt, h_start, (size_t)world * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    owner_scatter_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned long long*)d_keys, n, (uint32_t)world, d_cnt, (unsigned long long*)d_sorted, (long long*)d_dest);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_cnt);
+    return PG_OK;
+}
+
+extern "C" int pg_table_add_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n)
+{
+    if (!ctx || n < 0 || (n && !d_keys)) return fail(ctx, PG_ERR_INVALID, "pg_table_add_keys: bad argument");
+    CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
+    if (ctx->zero_markers) return fail(ctx, PG_ERR_STATE, "pg_table_add_keys: the table holds zero-count markers from pg_table_set - call pg_table_clear first");
+    int rc = ensure_table(ctx, std::max<int64_t>(n, 1));
+    if (rc) return rc;
+    ctx->counted = true;
+    // launches of < 2^31 keys, each followed by the gated clamp: a dense counter cannot wrap (table.cuh: saturation)
+    for (int64_t at = 0; at < n; at += (1ll << 30)) {
+        const int64_t m = std::min<int64_t>(1ll << 30, n - at);
+        table_add_keys_kernel<<<grid_for(m, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(view(ctx), ctx->mode, (const unsigned long long*)d_keys + at, m);
+        CK(saturate_if_flagged(ctx, true));
+    }
+    CK(cudaGetLastError());
+    return check_overflow(ctx);
+}
+
+extern "C" int pg_table_lookup_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, uint32_t* d_counts)
+{
+    if (!ctx || n < 0 || (n && (!d_keys || !d_counts))) return fail(ctx, PG_ERR_INVALID, "pg_table_lookup_keys: bad argument");
+    if (!n) return PG_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    { int rc_ = table_ready(ctx); if (rc_) return rc_; }
+    if (!ctx->have_table()) { CK(cudaMemsetAsync(d_counts, 0, (size_t)n * sizeof(uint32_t), ctx->stream)); return PG_OK; }
+    table_lookup_keys_kernel<<<grid_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(view(ctx), ctx->mode, (const unsigned long long*)d_keys, n, d_counts);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+// abundance tallies of the windows that start in words [w0, w1) from counts that came back from their owners:
+// d_dest (32 per word, from pg_keys_partition) indexes d_counts_sorted (the counts in the order the keys were sent)
+extern "C" int pg_features_add_counts(pg_ctx* ctx, pg_features* f, pg_batch* b, int64_t w0, int64_t w1, const int64_t* d_dest, const uint32_t* d_counts_sorted)
+{
+    if (!ctx || !f || !b || w0 < 0 || w1 < w0 || w1 > b->n_words) return fail(ctx, PG_ERR_INVALID, "pg_features_add_counts: bad argument");
+    if (!f->row_of_group || !b->wg || !b->gstart) return fail(ctx, PG_ERR_STATE, "pg_features_add_counts: the feature set must come from pg_featurize2(PG_FEAT_NO_ABUNDANCE) of this batch");
+    if (w1 == w0 || !f->rows) return PG_OK;
+    if (!d_dest || !d_counts_sorted) return fail(ctx, PG_ERR_INVALID, "pg_features_add_counts: null arrays");
+    CK(cudaSetDevice(ctx->p.device));
+    FeatParams P = {};
+    P.gstart = b->gstart; P.n_groups = f->n_groups; P.row_of_group = f->row_of_group; P.wg = b->wg;
+    P.vs = f->vs; P.td = f->td; P.ws = (uint32_t)ctx->p.window_size;
+    const uint64_t clamp64 = (uint64_t)P.ws * (uint64_t)P.vs;
+    P.clamp = clamp64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)clamp64;
+    P.use_magic = (P.ws > 1 && (uint64_t)P.ws * clamp64 < (1ull << 32)) ? 1 : 0;
+    P.magic = P.use_magic ? (uint32_t)(((1ull << 32) + P.ws - 1) / P.ws) : 0u;
+    P.abd = f->abd_raw; P.tnf = f->tnf_raw;
+    Timed t(ctx, T_FEAT, 1);
+    abd_from_counts_kernel<<<grid_for((w1 - w0) * 32, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(P, w0, w1, (const long long*)d_dest, d_counts_sorted);
+    CK(cudaGetLastError());
+    return PG_OK;
+}

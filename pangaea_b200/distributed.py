@@ -82,6 +82,80 @@ def extract_features_from_file(ctx: "_lib.Context", path, rank=None, world=None,
     return stream_mod.extract_features_streaming(ctx, open_stream, reduce_table=reduce_table)
 
 
+def _all_to_all(send, in_splits, out_splits, group):
+    """all_to_all_single on device tensors; backends without a CUDA all-to-all (gloo, used by the one-GPU tests) go through the host"""
+    import torch
+    import torch.distributed as dist
+
+    recv = torch.empty(int(sum(out_splits)), dtype=send.dtype, device=send.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, list(out_splits), list(in_splits), group=group)
+        return recv
+    h_send, h_recv = send.cpu(), torch.empty(int(sum(out_splits)), dtype=send.dtype)
+    dist.all_to_all_single(h_recv, h_send, list(out_splits), list(in_splits), group=group)
+    recv.copy_(h_recv)
+    return recv
+
+
+def extract_features_owner_partitioned(ctx: "_lib.Context", reads, group_keep, n_groups=None, group=None, seg_words=1 << 21):
+    """The north star's multi-GPU table: owner = hash(canonical k-mer) mod n_ranks, one all-to-all of keys for count insertion,
+    one all-to-all of keys + one of counts for the abundance queries (csrc/exchange.cuh).  This is the multi-rank form of the
+    HASH table (k > 16) - no dense view exists to all-reduce - and works for the dense table as well.  `reads`: this rank's
+    batch (pg_reads over host arrays, clouds whole - e.g. a shard of shard.plan_shards or a rank's byte range of a file).
+    Every rank's table ends up holding only the k-mers it owns.  Collective: every rank must call it with the same seg_words.
+    Returns Features for the rank's clouds."""
+    import torch
+    import torch.distributed as dist
+
+    L = _lib.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = f"cuda:{ctx.params.device}"
+    keep = np.ascontiguousarray(group_keep, dtype=np.uint8) if isinstance(group_keep, np.ndarray) else group_keep
+    ctx.table_clear()
+    batch = ctx.upload(reads)
+    n_words = int(L.pg_batch_n_words(batch.h))
+    # every rank runs the same number of exchange rounds (ranks with less data send empty segments)
+    rounds = torch.tensor([(n_words + seg_words - 1) // seg_words], dtype=torch.int64, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(rounds, op=dist.ReduceOp.MAX, group=group)
+    rounds = int(rounds)
+
+    def keys_by_owner(seg, feature):
+        w0 = min(n_words, seg * seg_words)
+        w1 = min(n_words, w0 + seg_words)
+        n = 32 * (w1 - w0)
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        ordered = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        dest = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        counts = np.zeros(world, dtype=np.int64)
+        ctx._ck(L.pg_batch_window_keys(ctx.h, batch.h, w0, w1, int(feature), keys.data_ptr()))
+        ctx._ck(L.pg_keys_partition(ctx.h, keys.data_ptr(), n, world, ordered.data_ptr(), dest.data_ptr(), counts.ctypes.data))
+        send_n = counts.tolist()
+        c = torch.tensor(send_n, dtype=torch.int64, device=dev)
+        recv_n = _all_to_all(c, [1] * world, [1] * world, group).tolist()  # how many keys every rank sends me
+        return w0, w1, ordered[: sum(send_n)], dest, send_n, recv_n
+
+    # ---- count: keys -> owners ----
+    for seg in range(rounds):
+        w0, w1, ordered, dest, send_n, recv_n = keys_by_owner(seg, feature=False)
+        mine = _all_to_all(ordered, send_n, recv_n, group)
+        ctx._ck(L.pg_table_add_keys(ctx.h, mine.data_ptr(), mine.numel()))
+        ctx.synchronize()
+    dist.barrier(group=group)  # every insert everywhere is done before the first query
+    # ---- featurize: grouping + TNF locally, counts from the owners ----
+    feats = ctx.featurize(batch, keep, n_groups, no_abundance=True)
+    for seg in range(rounds):
+        w0, w1, ordered, dest, send_n, recv_n = keys_by_owner(seg, feature=True)
+        queries = _all_to_all(ordered, send_n, recv_n, group)
+        answers = torch.empty(max(queries.numel(), 1), dtype=torch.int32, device=dev)
+        ctx._ck(L.pg_table_lookup_keys(ctx.h, queries.data_ptr(), queries.numel(), answers.data_ptr()))
+        back = _all_to_all(answers[: queries.numel()], recv_n, send_n, group)   # counts in the order the keys were sent
+        ctx._ck(L.pg_features_add_counts(ctx.h, feats.h, batch.h, w0, w1, dest.data_ptr(), back.data_ptr() if back.numel() else dest.data_ptr()))
+        ctx.synchronize()
+    feats.normalize()
+    batch.free()
+    return feats
+
+
 def gather_rows_named(names, feats: "_lib.Features", group=None):
     """Rank 0 gets (names, abundance int32, tnf int32) of all ranks in rank order (= file order); other ranks get None."""
     import torch.distributed as dist
