@@ -176,7 +176,8 @@ def design_bytes(n_bytes, entries_count, windows_feat, rows, sliced, vs=400, td=
         b["tnf"] = n_bytes * stream + 4.0 * rows * td
         if not shared:
             b["feat_scatter"] = n_bytes * stream + 4.125 * windows_feat
-        b["feat_apply"] = 4.125 * windows_feat + 4.0 * windows_feat + 4.0 * rows * vs
+        b["feat_apply"] = 4.0 * windows_feat + 4.0 * windows_feat + 4.0 * windows_feat  # entry in, u32 counter gathered, bin written back
+        b["feat_collect"] = 4.0 * windows_feat + 4.0 * rows * vs                            # entries in stream order, tallies out
     else:
         b["count_apply"] = n_bytes * stream + 8.0 * entries_count
         b["feat_apply"] = n_bytes * stream + 4.0 * windows_feat + out
@@ -185,12 +186,13 @@ def design_bytes(n_bytes, entries_count, windows_feat, rows, sliced, vs=400, td=
 
 KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,shared>", "count_split": "bucket_split_kernel",
                    "count_apply": "sub_apply_kernel", "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
-                   "feat_scatter": "bucket_scatter_kernel<15,feat>", "feat_apply": "bucket_apply_feat_kernel", "normalize": "normalize_rows_kernel"}
+                   "feat_scatter": "bucket_scatter_kernel<15,feat>", "feat_apply": "bucket_lookup_kernel", "feat_collect": "bucket_collect_kernel",
+                   "normalize": "normalize_rows_kernel"}
 STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_split", 9), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
-               ("normalize", 4))
+               ("feat_collect", 10), ("normalize", 4))
 # which §8d pass a kernel belongs to
 PASS_OF_STAGE = {"pack": "pack", "count_scatter": "count", "count_split": "count", "count_apply": "count", "feat_scatter": "featurize",
-                 "feat_apply": "featurize", "tnf": "featurize", "normalize": "rows_norm"}
+                 "feat_apply": "featurize", "feat_collect": "featurize", "tnf": "featurize", "normalize": "rows_norm"}
 
 
 def load_peaks():

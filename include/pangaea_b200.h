@@ -327,7 +327,8 @@ int pg_synth_generate2(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n
 /* ---- instrumentation -------------------------------------------------------- */
 /* device time (ms, CUDA events on the ctx stream) and launch count of the kernels run
  * since the last reset: which = 0 pack, 1 count (apply / direct), 2 group, 3 featurize (apply / direct),
- * 4 normalize, 5 all, 6 count scatter, 7 featurize scatter, 8 TNF, 9 count split (second partition level) */
+ * 4 normalize, 5 all, 6 count scatter, 7 featurize scatter, 8 TNF, 9 count split (second partition level),
+ * 10 featurize collect (collect.cuh: tallies from the looked-up entries, in stream order) */
 int pg_timing_reset(pg_ctx* ctx);
 int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* launches_out);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(HERE, "libpangaea_b200.
 
 PG_READ_CHANGE, PG_READ_NOFEAT = 1, 2
 PG_TABLE_AUTO, PG_TABLE_DENSE, PG_TABLE_HASH, PG_TABLE_NONE = 0, 1, 2, 3
-T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL, T_COUNT_SCATTER, T_FEAT_SCATTER, T_TNF, T_COUNT_SPLIT = range(10)
+T_PACK, T_COUNT, T_GROUP, T_FEAT, T_NORM, T_ALL, T_COUNT_SCATTER, T_FEAT_SCATTER, T_TNF, T_COUNT_SPLIT, T_COLLECT = range(11)
 ABD_RAW, TNF_RAW, ABD, TNF, WEIGHTS = range(5)
 PG_FQ_QUAL, PG_FQ_PINNED = 1, 2
 

@@ -32,8 +32,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lz"]
+    tmp = LIB + ".tmp"  # built beside the target and renamed into place: a snapshot of the tree never sees half a library
+    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES], "-lz"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -15,6 +15,7 @@
 
 #include "../../include/pangaea_b200.h"
 #include "bucket.cuh"
+#include "collect.cuh"
 #include "count.cuh"
 #include "count2.cuh"
 #include "exchange.cuh"
@@ -33,7 +34,7 @@ using namespace pg;
 // objects
 // ---------------------------------------------------------------------------
 // timing slots: one per kernel family (pg_timing_get `which`)
-enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_COUNT_SPLIT = 9, T_SLOTS = 10 };
+enum { T_PACK = 0, T_COUNT = 1, T_GROUP = 2, T_FEAT = 3, T_NORM = 4, T_ALL = 5, T_COUNT_SCATTER = 6, T_FEAT_SCATTER = 7, T_TNF = 8, T_COUNT_SPLIT = 9, T_COLLECT = 10, T_SLOTS = 11 };
 
 // grow-only device scratch kept by the ctx: the multi-GB partition buffers are allocated once, not once per step
 // (72 GB of cudaMallocAsync / cudaFreeAsync per step made the pool re-map memory: step times of 106 .. 380 ms)
@@ -87,6 +88,8 @@ struct pg_ctx {
     int tnf_overlap = 2;         // PG_TNF_OVERLAP=n: the TNF kernel runs on the second stream with n CTAs per SM, next to the look-up
                                  // sweep (0 = in line on the ctx stream)
     bool no_shared = false;      // PG_NO_SHARED=1: separate partitions for the count and featurize passes (A/B, tests)
+    int feat_path = -1;          // featurize pass of the sliced path: 1 = one sweep (gather + MATCH + RED per entry), 0 = lookup + collect
+                                 // (collect.cuh), -1 = by cloud size (PG_FEAT_APPLY=0/1 forces one of them)
     bool count_l2 = false;       // PG_COUNT_L2=1: apply the count entries with L2 atomics instead of the shared-memory sub-slices (A/B)
     int64_t count_seg_words = 1ll << 26; // segment of the count pass (2^31 windows: 13 GB of u32 + 6 GB of u16 entries); PG_SEG_WORDS overrides
     int64_t seg_words = 1ll << 26; // words per segment of the featurize pass: 2^31 windows -> 14 GB of u32 entries with the default
@@ -117,10 +120,11 @@ struct pg_batch {
     uint32_t* wg = nullptr;                    // n_words: word -> cloud map (sliced path)
     int64_t min_group_len = 0;
     // entries of the shared partition: written by pg_count, reused by pg_featurize (bucket.cuh: kScatterShared)
-    struct Segment { int64_t w0, w1; uint32_t* entries; int32_t* meta; unsigned long long* fill; BucketGeom geo; };
+    struct Segment { int64_t w0, w1; uint32_t* entries; int32_t* meta; unsigned long long* fill; uint2* runs; BucketGeom geo; };
     std::vector<Segment> stash;
     Workspace stash_ws;                        // backing store of all segments (borrowed from / returned to the ctx)
     uint32_t* stash_lost = nullptr;            // device flag: an overflow path bypassed the entry buffer
+    bool stash_sweep = true;                   // the kept entries are in the layout of the one-sweep featurize pass (runs padded to 32 + bases)
 };
 
 struct pg_features {
@@ -135,6 +139,7 @@ struct pg_features {
     int32_t* row_of_group = nullptr; // kept only by pg_featurize2(PG_FEAT_NO_ABUNDANCE): pg_features_add_counts maps cloud -> row with it
     int64_t n_groups = 0;
     bool normalized = false;
+    bool exported = false; // handed out through DLPack: a consumer may still have work queued on ITS stream when the last reference goes
 };
 
 static thread_local std::string g_err;
@@ -382,6 +387,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     { const char* e = getenv("PG_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = ctx->count_seg_words = atoll(e) / 512 * 512; }
     { const char* e = getenv("PG_COUNT_L2"); ctx->count_l2 = e && e[0] == '1'; }
     { const char* e = getenv("PG_NO_SHARED"); ctx->no_shared = e && e[0] == '1'; }
+    { const char* e = getenv("PG_FEAT_APPLY"); if (e && (e[0] == '0' || e[0] == '1')) ctx->feat_path = e[0] - '0'; }
     { const char* e = getenv("PG_TNF_OVERLAP"); if (e) ctx->tnf_overlap = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("PG_FEAT_SEG_WORDS"); if (e && atoll(e) >= 512) ctx->seg_words = atoll(e) / 512 * 512; }
     CKC(cudaMallocHost((void**)&ctx->h_pin, 8 * sizeof(int64_t)));
@@ -404,6 +410,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
+    CKC(cudaFuncSetAttribute(bucket_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(sub_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubWords * 4 + 16));
     CKC(cudaFuncSetAttribute(tnf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CKC(cudaFuncSetAttribute(tnf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -698,8 +705,19 @@ static BucketGeom bucket_geom(const pg_ctx* ctx, int64_t seg_words)
     geo.n_buckets = (int)(ctx->n_slots >> kSliceBits);
     geo.low_mask = (1u << kSliceBits) - 1u;
     const double mean = (double)seg_words * 32.0 / geo.n_buckets;
-    geo.cap = std::max<unsigned long long>(32ull, (((unsigned long long)(mean * ctx->region_slack) + 31ull) / 32ull) * 32ull);
+    const unsigned long long cap = (unsigned long long)(mean * ctx->region_slack);
+    geo.cap = std::max<unsigned long long>(32ull, ((cap + 31ull) / 32ull) * 32ull);
     return geo;
+}
+
+// Which featurize pass suits the batch?  Large clouds (the linked-read case: ~20 KB): one sweep - a warp's 32 entries fold into
+// ~10 REDs, 42.6 ms against 37 + 35 ms for lookup + collect at the headline workload.  Tiny clouds (one per read pair, hybrid
+// mode): lookup + collect - the sweep read-modify-writes every row from DRAM once per table slice (2.7 s against 0.7 + 0.6 s
+// at 300 M pairs).  profiles/bench_r02_c2_v3_*.json, bench_r02_c4_*.json.
+static bool use_sweep(const pg_ctx* ctx, int64_t n_bytes, int64_t n_groups)
+{
+    if (ctx->feat_path >= 0) return ctx->feat_path == 1;
+    return n_bytes / std::max<int64_t>(1, n_groups) >= 2048;
 }
 
 // grid of a scatter launch: every resident CTA walks tiles with a grid stride
@@ -777,7 +795,8 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
         if (rc) return rc;
         const BucketGeom pg = padded_geom(P.geo);
         const size_t n_seg = (size_t)((n_words + P.seg_words - 1) / P.seg_words);
-        const size_t per_seg = (size_t)pg.cap * pg.n_buckets * 4 + (size_t)pg.cap * pg.n_buckets / 32 * 4 + kMaxBuckets * sizeof(unsigned long long);
+        const size_t runs_bytes = (size_t)((P.seg_words + ScatterCfg<true>::kTileWords - 1) / ScatterCfg<true>::kTileWords) * kMaxBuckets * sizeof(uint2);
+        const size_t per_seg = (size_t)pg.cap * pg.n_buckets * 4 + (size_t)pg.cap * pg.n_buckets / 32 * 4 + kMaxBuckets * sizeof(unsigned long long) + runs_bytes;
         // as many leading segments as fit (a 125 M-pair batch has 12 of 14.6 GB each): the rest is partitioned per pass
         // leave room for what this step still allocates (level-2 entries, the scratch partitions of segments that are not
         // kept, the feature matrices) and 16 GB for the caller
@@ -804,6 +823,7 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
                     sgm.entries = (uint32_t*)(base + i * E * 4);
                     sgm.meta = (int32_t*)(base + n_keep * E * 4 + i * (E / 32) * 4);
                     sgm.fill = (unsigned long long*)(base + n_keep * E * 4 + n_keep * (E / 32) * 4 + i * kMaxBuckets * sizeof(unsigned long long));
+                    sgm.runs = (uint2*)(base + n_keep * E * 4 + n_keep * (E / 32) * 4 + n_keep * kMaxBuckets * sizeof(unsigned long long) + i * runs_bytes);
                     sgm.geo = pg;
                     b->stash.push_back(sgm);
                 }
@@ -855,7 +875,7 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
 {
     ScatterParams Q = {};
     Q.codes = b->codes; Q.mask = b->maskC; Q.k = ctx->p.k; Q.geo = P.geo; Q.st = ctx->d_bucket;
-    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat;
+    Q.entries = P.entries; Q.meta = nullptr; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat; Q.run_pad = 4u;
     Q.w0 = w0; Q.w1 = w1;
     FeatParams F = {};
     int rc = PG_OK;
@@ -863,7 +883,9 @@ static int count_segment(pg_ctx* ctx, CountPlan& P, pg_batch* b, int64_t w0, int
     if (P.shared && si < b->stash.size()) {
         if (b->stash[si].w0 != w0 || b->stash[si].w1 != w1) return fail(ctx, PG_ERR_STATE, "count pass: segment does not match the shared partition plan");
         const pg_batch::Segment& sgm = b->stash[si];
-        Q.entries = sgm.entries; Q.meta = sgm.meta; Q.lost = b->stash_lost;
+        Q.entries = sgm.entries; Q.lost = b->stash_lost; Q.runs = sgm.runs;
+        b->stash_sweep = use_sweep(ctx, b->n_bytes, b->n_groups);
+        if (b->stash_sweep) { Q.meta = sgm.meta; Q.run_pad = 32u; } // the sweep reads one base cloud per aligned group of 32 entries
         F.maskF = b->maskR ? b->maskR : b->maskF; F.wg = b->wg; F.gstart = b->gstart; F.n_groups = b->n_groups;
         {
             Timed t(ctx, T_COUNT_SCATTER, 3);
@@ -1316,24 +1338,55 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
                 }
                 if (covered < 0) { reuse = false; covered = 0; }
             }
-            if (reuse) {
-                for (auto& sgm : b->stash) {
-                    ctx->launches[T_GROUP] += 1; // the ticket reset, booked with the other housekeeping kernels
-                    bucket_reset_ticket_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_bucket);
+            // look-ups + tallies of one segment's entries: lookup (ordered sweep, bins written back in place) then collect (stream
+            // order, histograms in shared memory) - collect.cuh; PG_FEAT_APPLY=1 keeps the round-1 single sweep for A/B runs
+            const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
+            const int tile_bytes = ScatterCfg<true>::kTileWords * 32;
+            int c_slots = (int)std::min<size_t>(96, std::max<size_t>(4, (size_t)tile_bytes / avg_cloud + 3));
+            while (c_slots > 2 && ((size_t)c_slots * P.vs + c_slots) * 4 > 190 * 1024) --c_slots;
+            const size_t c_smem = ((size_t)c_slots * P.vs + c_slots) * 4;
+            int c_occ = 1;
+            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, bucket_collect_kernel, kCollectThreads, c_smem));
+            auto lookup_collect = [&](uint32_t* entries, const int32_t* meta, const uint2* runs, const BucketGeom& geo, const unsigned long long* fill,
+                                      int64_t w0, int64_t w1, bool shared_entries, bool sweep) {
+                ctx->launches[T_GROUP] += 1; // the ticket reset, booked with the other housekeeping kernels
+                bucket_reset_ticket_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_bucket);
+                if (sweep) {
                     Timed t(ctx, T_FEAT, 1);
-                    bucket_apply_feat_kernel<true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(sgm.entries, sgm.meta, sgm.geo, ctx->d_bucket, sgm.fill, P);
+                    if (shared_entries) bucket_apply_feat_kernel<true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, meta, geo, ctx->d_bucket, fill, P);
+                    else bucket_apply_feat_kernel<false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, meta, geo, ctx->d_bucket, nullptr, P);
+                    return;
                 }
+                {
+                    Timed t(ctx, T_FEAT, 1);
+                    if (shared_entries) bucket_lookup_kernel<true><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, fill, P);
+                    else bucket_lookup_kernel<false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(entries, geo, ctx->d_bucket, nullptr, P);
+                }
+                CollectParams C;
+                C.entries = entries; C.runs = reinterpret_cast<const RunRef*>(runs); C.geo = geo; C.w0 = w0; C.w1 = w1;
+                C.tile_words = ScatterCfg<true>::kTileWords; C.slots = c_slots; C.shared = shared_entries ? 1 : 0;
+                const int64_t n_tiles = (w1 - w0 + C.tile_words - 1) / C.tile_words;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * std::max(c_occ, 1)));
+                Timed t(ctx, T_COLLECT, 1);
+                bucket_collect_kernel<<<grid, kCollectThreads, c_smem, ctx->stream>>>(C, P);
+            };
+            if (reuse) {
+                for (auto& sgm : b->stash) lookup_collect(sgm.entries, sgm.meta, sgm.runs, sgm.geo, sgm.fill, sgm.w0, sgm.w1, true, b->stash_sweep);
             }
             if (covered < b->n_words) { // what pg_count did not keep (or everything): partition for this pass alone
                 const int64_t seg_words = std::min<int64_t>(b->n_words - covered, ctx->seg_words);
                 const BucketGeom geo = padded_geom(bucket_geom(ctx, seg_words));
                 const size_t E = (size_t)geo.cap * geo.n_buckets;
-                CKF(ws_get(ctx, ctx->ws_feat, E * 4 + E / 32 * 4));
+                const size_t runs_bytes = (size_t)((seg_words + ScatterCfg<true>::kTileWords - 1) / ScatterCfg<true>::kTileWords) * kMaxBuckets * sizeof(uint2);
+                CKF(ws_get(ctx, ctx->ws_feat, E * 4 + E / 32 * 4 + runs_bytes));
                 uint32_t* const feat_entries = (uint32_t*)ctx->ws_feat.p;
                 int32_t* const feat_meta = (int32_t*)((uint8_t*)ctx->ws_feat.p + E * 4);
+                uint2* const feat_runs = (uint2*)((uint8_t*)ctx->ws_feat.p + E * 4 + E / 32 * 4);
                 ScatterParams Q = {};
                 Q.codes = b->codes; Q.mask = P.maskF; Q.k = ctx->p.k; Q.geo = geo; Q.st = ctx->d_bucket;
-                Q.entries = feat_entries; Q.meta = feat_meta; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat;
+                Q.entries = feat_entries; Q.table = ctx->counts; Q.lost = nullptr; Q.sat = ctx->d_sat; Q.runs = feat_runs; Q.run_pad = 4u;
+                const bool sweep = use_sweep(ctx, b->n_bytes, n_groups);
+                if (sweep) { Q.meta = feat_meta; Q.run_pad = 32u; }
                 for (int64_t w0 = covered; w0 < b->n_words; w0 += seg_words) {
                     Q.w0 = w0; Q.w1 = std::min(b->n_words, w0 + seg_words);
                     {
@@ -1341,11 +1394,11 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
                         rc = scatter_launch<kScatterFeat>(ctx, Q, P);
                     }
                     if (rc) { cleanup(); pg_features_free(ctx, f); return rc; }
-                    Timed t(ctx, T_FEAT, 1);
-                    bucket_apply_feat_kernel<false><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(feat_entries, feat_meta, geo, ctx->d_bucket, nullptr, P);
+                    lookup_collect(feat_entries, feat_meta, feat_runs, geo, nullptr, Q.w0, Q.w1, false, sweep);
                 }
             }
             CKF(cudaGetLastError());
+            if (reuse && !b->stash_sweep) free_stash(ctx, b); // the look-up pass overwrote the kept entries with bins: they serve once
             cleanup();
             *out = f;
             return PG_OK;
@@ -1379,6 +1432,10 @@ static void features_release(pg_features* f, pg_ctx* ctx = nullptr)
 {
     if (f->refs.fetch_sub(1) > 1) return;
     cudaSetDevice(f->device);
+    // A DLPack consumer (torch) drops its tensor - and with it the last reference - as soon as Python lets go of it, even
+    // while kernels that read the buffer are still queued on the consumer's stream; a stream-ordered free on the ctx stream
+    // (or handing the block to the next allocation) would pull the memory from under them.
+    if (f->exported) cudaDeviceSynchronize();
     void* bufs[7] = { f->abd_raw, f->tnf_raw, f->abd, f->tnf, f->weights, f->group_of_row, f->row_of_group };
     for (void* p : bufs) {
         if (!p) continue;
@@ -1512,6 +1569,7 @@ extern "C" void* pg_features_dlpack(pg_ctx* ctx, pg_features* f, int which)
     }
     DlHolder* h = new DlHolder();
     h->f = f;
+    f->exported = true;
     ++f->refs;
     DLTensor& t = h->mt.dl_tensor;
     t.data = pg_features_device_ptr(f, which);

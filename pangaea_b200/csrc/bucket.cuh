@@ -56,22 +56,23 @@ constexpr uint32_t kInvalidEntry = 0xFFFFFFFFu; // never a real entry: count ent
 constexpr uint32_t kEntryIndexBits = 0x03FFFFF8u;
 constexpr int kMaxRowDelta = 509;      // 510 = count-only window of the shared partition, 511 = padding
 
-// tile shape of the scatter kernels: one word per thread
+// tile shape of the scatter kernels: one word per thread.  -DPG_FEAT_THREADS=256 builds the feature-format kernels with 256-word
+// tiles (four CTAs per SM); measured (profiles/bench_r02_scatter_ab.txt): scatter 19.2 -> 18.3 ms, but runs half as long cost the
+// second partition level and the collect kernel more than that.
+#ifndef PG_FEAT_THREADS
+#define PG_FEAT_THREADS 512
+#endif
 template <bool FEAT>
 struct ScatterCfg {
-    static constexpr int kThreads = FEAT ? 512 : 256;
+    static constexpr int kThreads = FEAT ? PG_FEAT_THREADS : 256;
     static constexpr int kTileWords = kThreads;
     // staging slots per slice per tile: mean = 32 * kThreads / 64 (128 / 256) + > 5 sigma of the binomial
-    static constexpr int kStageCap = FEAT ? 352 : 192;
+    static constexpr int kStageCap = kThreads == 512 ? 352 : 192;
     // words per staging row: + 4 so that consecutive rows start 4 banks apart (all rows fill at the same pace; with
     // a stride that is a multiple of 32 words the lanes of a store would crowd the banks of the current fill level)
     static constexpr int kStageStride = kStageCap + 4;
-    static constexpr int kMinCtas = FEAT ? 2 : 4;
-    // runs are padded with kInvalidEntry to a multiple of this, so that they start 16 B aligned and are copied
-    // out with 128-bit stores (feature runs: 32, because every aligned group of 32 entries shares one base row)
-    static constexpr uint32_t kRunPad = FEAT ? 32u : 4u;
+    static constexpr int kMinCtas = kThreads == 512 ? 2 : 4;
 };
-
 struct BucketGeom {
     int n_buckets;
     uint32_t low_mask;                   // (1 << kSliceBits) - 1
@@ -125,19 +126,20 @@ __device__ __forceinline__ uint32_t window_valid_mask(uint32_t mlo, uint32_t mhi
 //          scrambled index of kmer.cuh, y >> 26 its slice.
 // KT = 0: any k <= 15 at run time through kmer.cuh (same results, not tuned).
 // ---------------------------------------------------------------------------
-template <int KT, class Fn>
-__device__ __forceinline__ void for_each_window(uint64_t lo, uint64_t hi, int k_rt, Fn&& fn)
+// windows I0 .. I1 - 1 of the word (the rolling forward value restarts at I0)
+template <int KT, int I0, int I1, class Fn>
+__device__ __forceinline__ void for_window_range(uint64_t lo, uint64_t hi, int k_rt, Fn&& fn)
 {
     const uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi;
+    auto stream32 = [&](int i) { return i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32))); };
     if constexpr (KT == 15) {
         constexpr uint32_t M = 0x3FFFFFFFu, C = 0x2AAAAAAAu;
         constexpr uint32_t A8 = kMixA * 8u, K2 = 0u - (A8 << 15);
-        uint32_t f = fwd_of_window32(s0 & M, 15);
+        uint32_t f = fwd_of_window32(stream32(I0) & M, 15);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const uint32_t u = i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32)));
-            const uint32_t w = u & M;
-            if (i) f = ((f << 2) | (w >> 28)) & M;
+        for (int i = I0; i < I1; ++i) {
+            const uint32_t w = stream32(i) & M;
+            if (i > I0) f = ((f << 2) | (w >> 28)) & M;
             const uint32_t x = (w & 0x8000u) ? (w ^ C) : f;
             fn(i, x * A8 + (x >> 16) * K2);
         }
@@ -145,15 +147,20 @@ __device__ __forceinline__ void for_each_window(uint64_t lo, uint64_t hi, int k_
         const int k = k_rt;
         const uint32_t wmask = (uint32_t)low_mask64(2 * k);
         const int top = 2 * (k - 1);
-        uint32_t f = fwd_of_window32(s0 & wmask, k);
+        uint32_t f = fwd_of_window32(stream32(I0) & wmask, k);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const uint32_t u = i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32)));
-            const uint32_t w = u & wmask;
-            if (i) f = ((f << 2) | ((w >> top) & 3u)) & wmask;
+        for (int i = I0; i < I1; ++i) {
+            const uint32_t w = stream32(i) & wmask;
+            if (i > I0) f = ((f << 2) | ((w >> top) & 3u)) & wmask;
             fn(i, dense_index_of_pair(f, w ^ (0xAAAAAAAAu & wmask), k) << 3);
         }
     }
+}
+
+template <int KT, class Fn>
+__device__ __forceinline__ void for_each_window(uint64_t lo, uint64_t hi, int k_rt, Fn&& fn)
+{
+    for_window_range<KT, 0, 32>(lo, hi, k_rt, fn);
 }
 
 // same value for one window, not unrolled (slow paths)
@@ -254,6 +261,10 @@ struct ScatterParams {
     uint32_t* lost;            // shared: set to 1 when an overflow path applied counts directly - the entries of those
                                // windows are missing from the buffer, so the featurize pass must not reuse it
     uint32_t* sat;             // count / shared: raised when a direct add takes a counter to bit 31 (table.cuh: saturation)
+    uint32_t run_pad;          // runs are padded with kInvalidEntry to a multiple of this many entries: 4 (16 B, what the copy engine
+                               // needs) or 32 together with `meta` (the round-1 sweep reads one base per aligned group of 32)
+    uint2* runs;               // feature / shared (optional): [tile][kMaxBuckets] = (offset of the tile's run inside the region, live entries) -
+                               // lets collect.cuh walk the entries in stream order again
 };
 
 // MODE of the scatter kernel
@@ -377,13 +388,9 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             const uint32_t v = trip == 0 ? v0 : trip == 1 ? v1 : v2;
             const uint32_t d = trip == 0 ? d0 : trip == 1 ? d1 : delta_bits(kDeltaCountOnly);
             if (v == 0u) continue; // trips 1 and 2 are rare: one word per cloud / lower-case bases
-            // ptxas would hoist the 32 loop-invariant window extractions out of this loop and spill them: a shuffle
-            // from the own lane is the identity, but not one the optimiser can see through (2 SHFL per 32 windows)
-            lo = __shfl_sync(__activemask(), lo, lane);
-            hi = __shfl_sync(__activemask(), hi, lane);
             // four windows at a time: the four returning atomics are issued back to back, so their latency overlaps
             uint32_t yb[4];
-            for_each_window<KT>(lo, hi, k, [&](int i, uint32_t y) {
+            auto hand_out = [&](int i, uint32_t y) {
                 yb[i & 3] = y;
                 if ((i & 3) != 3) return;
                 uint32_t bk[4], slot[4];
@@ -397,7 +404,12 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                     PG_CHECK(bk[q] <= (uint32_t)kMaxBuckets && (bk[q] == (uint32_t)kMaxBuckets || (int)bk[q] < Q.geo.n_buckets));
                     stage[bk[q] * STRIDE + min(slot[q], (uint32_t)(CAP - 1))] = FEAT ? ((yb[q] & kEntryIndexBits) | d) : yb[q];
                 }
-            });
+            };
+            // ptxas would hoist the 32 loop-invariant window extractions out of the trip loop and spill them: a shuffle
+            // from the own lane is the identity, but not one the optimiser can see through (2 SHFL per 32 windows)
+            lo = __shfl_sync(__activemask(), lo, lane);
+            hi = __shfl_sync(__activemask(), hi, lane);
+            for_each_window<KT>(lo, hi, k, hand_out);
         }
         bulk_store_fence(); // the rows were written through the generic proxy; the copy engine reads them through the async proxy
         __syncthreads();
@@ -406,10 +418,11 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
         // ---- claim one run per slice in the entry buffer and hand it to the copy engine: lane <-> slice ----
         if (warp < 2) {
             const int b = 32 * warp + lane;
+            uint2 run = make_uint2(0u, 0u);
             if (b < Q.geo.n_buckets) {
                 const uint32_t c = cnt[b];
                 const uint32_t n = c > (uint32_t)CAP ? 0u : c; // a row that overflowed is redone below
-                const uint32_t n_pad = (n + Cfg::kRunPad - 1u) & ~(Cfg::kRunPad - 1u);
+                const uint32_t n_pad = (n + Q.run_pad - 1u) & ~(Q.run_pad - 1u);
                 if (n) {
                     uint32_t* row = stage + b * STRIDE;
                     const unsigned long long off = atomicAdd(&Q.st->cursors[b], (unsigned long long)n_pad);
@@ -419,7 +432,8 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                         for (uint32_t e = n; e < n_pad; ++e) row[e] = kInvalidEntry; // (CAP is a multiple of the padding: it fits)
                         bulk_store_fence();
                         bulk_store(Q.entries + gb, row, n_pad * 4u, policy);
-                        if (FEAT) for (uint32_t i = 0; i < (n_pad >> 5); ++i) Q.meta[(gb >> 5) + i] = tile_base;
+                        if (FEAT && Q.meta) for (uint32_t i = 0; i < (n_pad >> 5); ++i) Q.meta[(gb >> 5) + i] = tile_base;
+                        run = make_uint2((uint32_t)off, n);
                     } else { // region full (pathological repeats): this lane applies / looks up the run itself
                         atomicMin(&Q.st->limits[b], off);
                         for (uint32_t e = 0; e < n; ++e) {
@@ -437,6 +451,7 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                     }
                 }
             }
+            if (FEAT && Q.runs) Q.runs[t * kMaxBuckets + b] = run; // (runs that took an overflow path stay empty: their tallies were made directly)
             bulk_commit();
         }
 

@@ -1,6 +1,6 @@
 # round 2, call C: tools tests, default bench (pread staging), ncu launch list + full capture of the count-side kernels
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_tools.py tests/test_gpu_ingest.py -m gpu -q > gpurun_out/pytest_c.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_c.log
+timeout 1200 python -m pytest tests/test_gpu_tools.py tests/test_gpu_ingest.py tests/test_gpu_multi.py -m gpu -q > gpurun_out/pytest_c.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_c.log
 tail -25 gpurun_out/pytest_c.log
 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_last.log 2> gpurun_out/bench_last.err; echo "bench exit $?"
 python - <<'PY'
