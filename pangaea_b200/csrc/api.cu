@@ -1488,9 +1488,15 @@ extern "C" int pg_normalize(pg_ctx* ctx, pg_features* f)
     CK(dmalloc(ctx, &f->weights, (size_t)f->rows));
     if (f->rows) {
         Timed t(ctx, T_NORM, 2);
-        const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
-        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
-        normalize_rows_kernel<<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
+        if (f->rows >= (1 << 20)) { // millions of rows: four of them per warp in flight
+            const int grid = grid_for(f->rows * 8, 256, ctx->sm_count * 8);
+            normalize_rows_kernel<8><<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
+            normalize_rows_kernel<8><<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
+        } else {
+            const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
+            normalize_rows_kernel<32><<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
+            normalize_rows_kernel<32><<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
+        }
     }
     CK(cudaGetLastError());
     f->normalized = true;

@@ -29,23 +29,27 @@ __host__ __device__ __forceinline__ unsigned long long text_round6(uint32_t v)
     return (unsigned long long)base + (up ? q : 0u); // (64-bit: 4294967295 rounds to 4294970000)
 }
 
+// LPR lanes per row: a full warp for few long rows, 8 lanes (four rows per warp in flight) when there are millions of rows
+template <int LPR>
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, float* __restrict__ out, double* __restrict__ weights, int text_round)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int lane = threadIdx.x & (LPR - 1);
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) / LPR; // row groups in flight
+    for (int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR; r0 < ((rows + 32 / LPR - 1) / (32 / LPR)) * (32 / LPR); r0 += warps) {
+        const bool have = r0 < rows;            // (the groups of a warp stay together for the shuffles)
+        const int64_t r = have ? r0 : rows - 1;
         const uint32_t* src = raw + r * dim;
         unsigned long long sum = 0;
         unsigned long long mx = 0;
-        for (int j = lane; j < dim; j += 32) {
+        for (int j = lane; j < dim; j += LPR) {
             unsigned long long v = __ldg(src + j);
             if (text_round) v = text_round6((uint32_t)v);
             sum += v;
             mx = max(mx, v);
         }
 #pragma unroll
-        for (int d = 16; d; d >>= 1) {
+        for (int d = LPR / 2; d; d >>= 1) {
             sum += __shfl_xor_sync(0xffffffffu, sum, d);
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
         }
@@ -64,8 +68,9 @@ normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, f
             const double rem = fma(-norm, q, x);
             return fma(rem, y, q);
         };
+        if (!have) continue;
         float* dst = out + r * dim;
-        for (int j = lane; j < dim; j += 32) {
+        for (int j = lane; j < dim; j += LPR) {
             unsigned long long v = __ldg(src + j);
             if (text_round) v = text_round6((uint32_t)v);
             dst[j] = (float)quot(v);

@@ -48,7 +48,9 @@ tnf_kernel(const FeatParams P)
     for (int64_t tile = w_begin; tile < w_end; tile += kTnfThreads) {
         const int64_t tile_end = min(tile + (int64_t)kTnfThreads, w_end);
         const uint32_t g_lo = __ldg(P.wg + tile) & ~kWordMixed;
-        const uint32_t g_hi = __ldg(P.wg + tile_end - 1) & ~kWordMixed; // clouds of the uniform words: g_lo .. g_hi
+        const uint32_t gw_last = __ldg(P.wg + tile_end - 1);
+        const uint32_t g_hi = (gw_last & ~kWordMixed) + ((gw_last & kWordMixed) ? 1u : 0u); // clouds of the tile: g_lo .. g_hi (a cloud that
+                                                                                             // starts inside the last word included)
         const int64_t j = tile + threadIdx.x;
         if (j + kTnfThreads < w_end) { // next tile of this CTA -> L2 while this one is tallied
             if ((threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.codes + j + kTnfThreads));
@@ -88,8 +90,27 @@ tnf_kernel(const FeatParams P)
                     }
                 }
             } else if (tvalid != 0u) {
-                // a cloud boundary inside the word: resolve the cloud per position
                 const uint64_t lo = __ldg(P.codes + j), hi = __ldg(P.codes + j + 1);
+                // a cloud boundary inside the word.  The usual case - ONE boundary, both clouds have bins in shared memory - is
+                // tallied like any other word (with one cloud per read pair every tenth word is of this kind: 10 % of the
+                // positions going to the global matrix one RED at a time cost that configuration 1 s per 300 M pairs)
+                const uint32_t slot = g - g_lo;
+                const bool third = (int64_t)g + 2 < P.n_groups && __ldg(P.gstart + g + 2) < (j + 1) * 32;
+                if (!third && slot + 1u < (uint32_t)n_slots) {
+                    const int split = (int)(__ldg(P.gstart + g + 1) - j * 32); // first base of the second cloud, 1 .. 31
+                    const bool ok0 = __ldg(P.row_of_group + g) >= 0, ok1 = __ldg(P.row_of_group + g + 1) >= 0;
+                    const uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi;
+                    const uint32_t first = (1u << split) - 1u;
+                    const uint32_t live = tvalid & ((ok0 ? first : 0u) | (ok1 ? ~first : 0u));
+                    uint32_t* my = bins + slot * nb;
+                    const uint32_t dmy = dummy - slot * nb;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t u = i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32)));
+                        atomicAdd(my + ((live & (1u << i)) ? (u & tmask) + (i >= split ? (uint32_t)nb : 0u) : dmy), 1u);
+                    }
+                } else {
+                // three clouds in one word (clouds shorter than 32 bases) or no bins left: resolve the cloud per position
                 int64_t gg = g;
                 int64_t next_start = __ldg(P.gstart + gg + 1);
                 int32_t row = __ldg(P.row_of_group + gg);
@@ -103,6 +124,7 @@ tnf_kernel(const FeatParams P)
                     if (row < 0 || !((tvalid >> i) & 1u)) continue;
                     const uint32_t u = (uint32_t)(i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo);
                     atomicAdd(P.tnf + (int64_t)row * P.td + lut_s[u & tmask], 1u);
+                }
                 }
             }
         }

@@ -90,6 +90,8 @@ def _all_to_all(send, in_splits, out_splits, group):
     recv = torch.empty(int(sum(out_splits)), dtype=send.dtype, device=send.device)
     if dist.get_backend(group) == "nccl":
         dist.all_to_all_single(recv, send, list(out_splits), list(in_splits), group=group)
+        # the collective is ordered on torch's stream; what consumes `recv` runs on the ctx stream, which is not ordered after it
+        torch.cuda.current_stream(send.device).synchronize()
         return recv
     h_send, h_recv = send.cpu(), torch.empty(int(sum(out_splits)), dtype=send.dtype)
     dist.all_to_all_single(h_recv, h_send, list(out_splits), list(in_splits), group=group)
