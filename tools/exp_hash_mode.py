@@ -6,7 +6,7 @@ from pangaea_b200 import _lib
 from bench import make_synthetic_batch
 for k, cap in ((21, 1 << 31), (31, 1 << 31)):
     ctx = _lib.Context(device=0, k=k, table_capacity=cap)
-    s = make_synthetic_batch(ctx, 10_000_000, 100, seed=2)
+    s = make_synthetic_batch(ctx, 10_000_000, read_len=100, seed=2)
     keep = np.ones(s["n_groups"], np.uint8); keep[0] = 0
     for it in range(3):
         if it == 1:
