@@ -626,6 +626,12 @@ def run_streamed(env):
             e.record()
         return e
 
+    # the batches keep the partition of their windows for the featurize pass when all of them fit beside the packed batches
+    # (the same rule as pangaea_b200/stream.py: keep_partitions)
+    from pangaea_b200 import stream as stream_mod
+
+    keep_part = n_batches == 1 or (ppb > 1 and stream_mod.keep_partitions(ctx, 2.0 * pairs * (cfg["read_len"] + 1)))
+
     def one_step(collect=None):
         """-> (ms timed on this rank, rows, checksum).  Generation of a batch is outside the timed spans."""
         spans = []
@@ -635,7 +641,7 @@ def run_streamed(env):
             bd = gen(i)
             a = span()
             b = ctx.adopt(bd["reads"])
-            ctx.count(b, keep_partition=n_batches == 1)
+            ctx.count(b, keep_partition=keep_part)
             if n_batches > 1:
                 b.compact()
             z = span()
@@ -706,7 +712,7 @@ def run_streamed(env):
     n_bytes = 2 * pairs * (cfg["read_len"] + 1)
     windows = int(r[1]) // world
     roofline = build_roofline(stage_ms, stage_launches, pairs, cfg["read_len"], rows, n_bytes, windows, windows, value / world)
-    config = dict(config, batches_per_gpu=int(n_batches), batch_pairs=int(bp),
+    config = dict(config, batches_per_gpu=int(n_batches), batch_pairs=int(bp), partitions_kept=bool(keep_part),
                   timing="sum of CUDA-event spans around the processing of each batch (count pass, all-reduce, featurize pass), max over ranks; "
                          "batches are generated on the device between the spans")
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

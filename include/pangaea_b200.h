@@ -108,9 +108,9 @@ int pg_batch_adopt(pg_ctx* ctx, const pg_reads* dev, pg_batch** out);
 void pg_batch_free(pg_ctx* ctx, pg_batch* b);
 /* one batch of a stream: pg_batch_upload + pg_count2 with the copy overlapped chunk by chunk; the table is NOT cleared */
 int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep_partition, pg_batch** out);
-/* release the ASCII bases (and a kept partition): the 2-bit stream, masks and read offsets - 0.5 B per base + 9 B per
- * read - stay, which is all pg_featurize needs.  Lets the batches of a file larger than HBM's ASCII capacity wait
- * on the device for the featurize pass. */
+/* release the ASCII bases: the 2-bit stream, masks and read offsets - 0.5 B per base + 9 B per read - stay, which is
+ * all pg_featurize needs (a partition kept by pg_count2 stays too: ~4.5 B per k-mer window).  Lets the batches of a file
+ * larger than HBM's ASCII capacity wait on the device for the featurize pass. */
 int pg_batch_compact(pg_ctx* ctx, pg_batch* b);
 int64_t pg_batch_n_groups(const pg_batch* b); /* 1 + number of PG_READ_CHANGE flags */
 /* shape of a batch and its arrays back on the host (tests, debugging; a compacted batch has no bases left: seq_out must be NULL) */

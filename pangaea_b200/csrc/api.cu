@@ -81,7 +81,8 @@ struct pg_ctx {
     BigCache big;
     Workspace ws_text[2];                       // device staging of the text chunks of pg_ingest_text: filled on the copy stream while
     int text_toggle = 0;                        // the compute stream still works on the batch before (two, used alternately)
-    Workspace ws_stash;                         // one cached shared-partition buffer (taken by a batch in pg_count, returned by pg_batch_free)
+    std::vector<Workspace> stash_pool;          // idle shared-partition buffers (one is taken by a batch in pg_count and returned by pg_batch_free;
+                                                // the batches of a stream that keep their partitions hold one each)
     BucketState* d_bucket = nullptr; // cursors / limits / ticket of the L2-sliced path
     double region_slack = 1.5;       // region capacity = slack x mean entries per slice (PG_REGION_SLACK overrides; tests force overflow)
     bool force_direct = false;   // PG_FORCE_DIRECT=1: never use the L2-sliced path (A/B measurements)
@@ -429,7 +430,8 @@ extern "C" void pg_destroy(pg_ctx* ctx)
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
     for (auto& kv : ctx->big.free_blocks) cudaFree(kv.second); // (live blocks belong to batches / feature sets still around)
-    cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p); cudaFree(ctx->ws_stash.p);
+    cudaFree(ctx->ws_entries.p); cudaFree(ctx->ws_entries2.p); cudaFree(ctx->ws_feat.p);
+    for (auto& w : ctx->stash_pool) cudaFree(w.p);
     cudaFree(ctx->ws_text[0].p); cudaFree(ctx->ws_text[1].p);
     cudaFree(ctx->counts); cudaFree(ctx->slots); cudaFree(ctx->d_lut); cudaFree(ctx->d_overflow); cudaFree(ctx->d_sat); cudaFree(ctx->d_scalar); cudaFree(ctx->d_bucket);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -457,7 +459,9 @@ extern "C" int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_byte
     CK(cudaSetDevice(ctx->p.device));
     size_t f = 0, t = 0;
     CK(cudaMemGetInfo(&f, &t));
-    *free_bytes = (int64_t)(available_bytes(ctx) + ctx->big.free_bytes + ctx->ws_stash.bytes);
+    size_t idle = 0;
+    for (auto& w : ctx->stash_pool) idle += w.bytes;
+    *free_bytes = (int64_t)(available_bytes(ctx) + ctx->big.free_bytes + idle);
     *total_bytes = (int64_t)t;
     return PG_OK;
 }
@@ -630,9 +634,8 @@ extern "C" int pg_batch_download(pg_ctx* ctx, const pg_batch* b, uint8_t* seq_ou
 static void free_stash(pg_ctx* ctx, pg_batch* b)
 {
     b->stash.clear();
-    if (b->stash_ws.p) { // back to the ctx (later use is ordered on the same stream), or released when the ctx already holds one
-        if (!ctx->ws_stash.p) ctx->ws_stash = b->stash_ws;
-        else { cudaStreamSynchronize(ctx->stream); cudaFree(b->stash_ws.p); }
+    if (b->stash_ws.p) { // back to the ctx (later use is ordered on the same stream)
+        ctx->stash_pool.push_back(b->stash_ws);
         b->stash_ws = Workspace();
     }
     dfree(ctx, b->stash_lost);
@@ -801,17 +804,25 @@ static int count_plan_init(pg_ctx* ctx, pg_batch* b, CountPlan& P, bool packed =
         // leave room for what this step still allocates (level-2 entries, the scratch partitions of segments that are not
         // kept, the feature matrices) and 16 GB for the caller
         size_t n_keep = n_seg;
-        if (n_seg * per_seg > ctx->ws_stash.bytes) { // the cached buffer is too small: how much may it grow?  (steady-state
+        // an idle buffer of the pool: the smallest that is large enough, else the largest (it is grown below)
+        int pick = -1;
+        for (int i = 0; i < (int)ctx->stash_pool.size(); ++i) {
+            const size_t have = ctx->stash_pool[(size_t)i].bytes, best = pick < 0 ? 0 : ctx->stash_pool[(size_t)pick].bytes;
+            const bool fits = have >= n_seg * per_seg, best_fits = pick >= 0 && best >= n_seg * per_seg;
+            if (pick < 0 || (fits && (!best_fits || have < best)) || (!fits && !best_fits && have > best)) pick = i;
+        }
+        Workspace idle = pick >= 0 ? ctx->stash_pool[(size_t)pick] : Workspace();
+        if (n_seg * per_seg > idle.bytes) { // no idle buffer is large enough: how much may one grow?  (steady-state
             // steps never get here - the memory queries below were seen to stall a step for tens of ms on a fresh box)
-            const size_t avail = available_bytes(ctx) + ctx->ws_stash.bytes;
+            const size_t avail = available_bytes(ctx) + idle.bytes;
             const size_t reserve = 3 * per_seg + ((size_t)16 << 30);
-            const size_t budget = std::max<size_t>(ctx->ws_stash.bytes, avail > reserve ? (size_t)(0.85 * (double)(avail - reserve)) : 0);
+            const size_t budget = std::max<size_t>(idle.bytes, avail > reserve ? (size_t)(0.85 * (double)(avail - reserve)) : 0);
             n_keep = std::min<size_t>(n_seg, budget / per_seg);
         }
         if (const char* e = getenv("PG_STASH_SEGMENTS")) n_keep = std::min<size_t>(n_keep, (size_t)std::max(0, atoi(e))); // tests: force a partial stash
         if (b->min_group_len >= 64 && (packed || !b->nofeat) && n_keep > 0) {
-            b->stash_ws = ctx->ws_stash; // borrow the cached buffer (grown if too small)
-            ctx->ws_stash = Workspace();
+            b->stash_ws = idle; // borrow the buffer (grown if too small)
+            if (pick >= 0) ctx->stash_pool.erase(ctx->stash_pool.begin() + pick);
             if (ws_get(ctx, b->stash_ws, n_keep * per_seg) == cudaSuccess) {
                 P.shared = true;
                 P.geo = pg;
@@ -1287,7 +1298,8 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
                 const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
                 const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
                 P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
-                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb;
+                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2 + P.td) * sizeof(uint32_t) + 2 * nb;
+                P.tnf_store = b->min_group_len >= 64 ? 1 : 0; // (no word holds three clouds then: every boundary word of a whole cloud is tallied in shared memory)
                 // The TNF kernel is bound by shared-memory atomics, the look-up sweep below by L1 gathers: with a few CTAs per SM
                 // on the second stream it runs NEXT TO the sweep instead of before it.
                 const bool side = ctx->tnf_overlap > 0;
@@ -1700,8 +1712,7 @@ extern "C" int pg_batch_compact(pg_ctx* ctx, pg_batch* b)
         b->read_off = off; b->read_flag = flag; b->owns_meta = true;
         CK(cudaStreamSynchronize(ctx->stream)); // the caller's buffers are free to go when this returns
     }
-    b->seq = b->qual = nullptr;
-    free_stash(ctx, b);
+    b->seq = b->qual = nullptr; // (a kept partition stays: pg_count2's keep_partition decides about it)
     return PG_OK;
 }
 

@@ -113,11 +113,25 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
         CKI(cudaStreamWaitEvent(ctx->stream, ev, 0));
         ctx->pool.push_back(ev);
     }
+    // PG_INGEST_DEBUG=1: wall time of every phase on stderr (each mark waits for the stream)
+    static const bool dbg = getenv("PG_INGEST_DEBUG") && getenv("PG_INGEST_DEBUG")[0] == '1';
+    double t_last = 0;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    if (dbg) { cudaStreamSynchronize(ctx->stream); t_last = now_ms(); }
+    auto mark = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double t = now_ms();
+        fprintf(stderr, "[ingest] %-12s %7.2f ms\n", what, t - t_last);
+        t_last = t;
+    };
+    mark("h2d");
     long long* line_start = nullptr;
     int64_t n_lines = 0;
     int rc = build_line_index(ctx, d_text, n_bytes, &line_start, &n_lines);
     if (rc) return done(rc);
     tmp.push_back(line_start);
+    mark("line index");
     // whole records only, unless this is the end of the input (a trailing partial record still yields its reads)
     int64_t n_rec = final_chunk ? (n_lines + 7) / 8 : n_lines / 8;
     if (!final_chunk) { // complete lines only: an unterminated last line belongs to the next chunk
@@ -171,6 +185,7 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
     barcode_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, latch, bc_off, bc_len);
     reads_kernel<<<g_rec, 256, 0, ctx->stream>>>(T, n_rec, bc_off, bc_len, d_carry, (int)last_len, read_bytes, flag2, change);
     CKI(cudaGetLastError());
+    mark("headers");
 
     // ---- where does this batch end?  at the last cloud flush, or anywhere inside a cloud labelled "" ----
     int64_t n_use = n_rec;
@@ -188,6 +203,7 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
             if (last_bc_len != 0 && last_flush != n_rec - 1) n_use = last_flush + 1; // (0 when the chunk holds no flush: the caller widens it)
         }
     }
+    mark("cut point");
     if (n_use == 0) { delete info; *consumed_out = 0; pg_batch* none = nullptr; *batch_out = none; *info_out = nullptr; return done(PG_OK); }
 
     // ---- the batch: read offsets, sequence bytes, flags ----
@@ -211,8 +227,10 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
     copy_reads_kernel<<<g_copy, 256, 0, ctx->stream>>>(T, n_use, read_start, read_bytes, b->seq);
     if (want_q) copy_quals_kernel<<<g_copy, 256, 0, ctx->stream>>>(T, n_use, read_start, read_bytes, b->qual);
     CKI(cudaGetLastError());
+    mark("copy reads");
     rc = pack_range(ctx, b, 0, b->n_words + 2);
     if (rc) { delete info; pg_batch_free(ctx, b); return done(rc); }
+    mark("pack");
 
     // ---- labels of the clouds this batch opens ----
     int64_t n_lab = 0;
@@ -245,6 +263,7 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
     for (size_t g = 0; g < info->labels.size(); ++g) info->keep[g] = info->labels[g].empty() ? 0 : 1;
     if (!*read_type_io && latch != ~0ull && (int64_t)(latch >> 2) < n_use) *read_type_io = (int32_t)(latch & 3ull);
     CKI(cudaStreamSynchronize(ctx->stream));
+    mark("labels");
 #undef CKI
     *batch_out = b; *info_out = info;
     return done(PG_OK);

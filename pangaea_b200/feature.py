@@ -97,8 +97,11 @@ class Feature:
             path1, path2, min_qual = self._inputs()
             ctx = _lib.Context(device=self.device, k=int(self.kmer), tnf_k=int(self.tnf_k), window_size=int(self.ws),
                                vector_size=int(self.vs), min_length=int(self.minl), min_qual_char=min_qual)
+            size = sum(os.path.getsize(p) for p in (path1, path2) if p)
+            hint = None if str(path1).endswith(".gz") else 0.45 * size  # (sequence lines are ~40 % of a plain FASTQ's bytes)
             names, feats = stream_mod.extract_features_streaming(
-                ctx, lambda: _lib.FastqStream(path1, path2, want_qual=bool(min_qual), pinned=True, target_seq_bytes=self.batch_seq_bytes))
+                ctx, lambda: _lib.FastqStream(path1, path2, want_qual=bool(min_qual), pinned=True, target_seq_bytes=self.batch_seq_bytes),
+                seq_bytes_hint=hint)
             names = np.array(names, dtype=object)
             abd32, tnf32 = feats.raw()
             abundance, tnf = abd32.astype(np.int64), tnf32.astype(np.int64)

@@ -24,6 +24,15 @@ from . import _lib
 DEFAULT_BATCH_SEQ_BYTES = 6 << 30
 
 
+def keep_partitions(ctx, seq_bytes_total) -> bool:
+    """May the batches of a stream keep the partition of their k-mer windows (what pg_count2's keep_partition asks for) until the
+    featurize pass?  Yes when all of them plus the packed batches fit in about half of the device memory - the featurize pass then
+    skips its own partition (a fifth of its time); the rest is for entries in flight and the matrices.  A kept partition is
+    allocated at region capacity: 4 B per base position x 1.5 slack x 1.08 padding = 6.5 B per sequence byte."""
+    _, total = ctx.mem_info()
+    return seq_bytes_total * (6.5 + 0.6) < 0.5 * total
+
+
 class _Prefetch:
     """iterate a FastqStream one batch ahead on a feeder thread (pg_fastq_stream_next releases the GIL)"""
 
@@ -135,7 +144,7 @@ def _size(path):
     return os.path.getsize(path)
 
 
-def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=True, reduce_table=None, resident_fraction=0.45):
+def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=True, reduce_table=None, resident_fraction=0.45, seq_bytes_hint=None):
     """Whole path over a stream of batches.
 
     open_stream: callable -> a fresh _lib.FastqStream (called again for pass 2 when the packed batches do not fit).
@@ -172,10 +181,11 @@ def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=Tru
 
     # ---- pass 1: count every batch ----
     held, resident, keep_resident = [], 0, True
+    keep_part = seq_bytes_hint is not None and keep_partitions(ctx, seq_bytes_hint)
 
     def count_one(fq):
         nonlocal resident, keep_resident
-        b = ctx.upload_count(fq.reads, keep_partition=False)
+        b = ctx.upload_count(fq.reads, keep_partition=keep_part)
         ctx.synchronize()  # the copies read fq's host buffers
         packed = fq.reads.n_bytes // 2 + 9 * fq.reads.n_reads
         if keep_resident and resident + packed > budget:
@@ -229,7 +239,8 @@ def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=Tru
     return names, feats
 
 
-def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 30, clear_table=True, reduce_table=None, resident_fraction=0.45):
+def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 30, clear_table=True, reduce_table=None, resident_fraction=0.45,
+                                   byte_range=None):
     """The same two-pass flow with the DEVICE parser (DeviceIngest) as the source of batches - plain-text interleaved FASTQ
     only; gzip, paired or hostile input goes through extract_features_streaming.  Returns (names list[str], Features)."""
     if clear_table:
@@ -237,9 +248,10 @@ def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 
     _, total = ctx.mem_info()
     budget = int(total * resident_fraction)
     held, resident, keep_resident = [], 0, True
+    keep_part = keep_partitions(ctx, 0.45 * _size(path))  # (sequence lines are ~40 % of a FASTQ file's bytes)
     for batch, keep, labels, is_last in DeviceIngest(ctx, path, window_bytes):
         single = is_last and not held
-        ctx.count(batch, keep_partition=single)
+        ctx.count(batch, keep_partition=single or keep_part)
         n_reads, n_bytes = batch.shape()
         packed = n_bytes // 2 + 9 * n_reads
         if keep_resident and not single and resident + packed > budget:
