@@ -1298,8 +1298,7 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
                 const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
                 const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
                 P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
-                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2 + P.td) * sizeof(uint32_t) + 2 * nb;
-                P.tnf_store = b->min_group_len >= 64 ? 1 : 0; // (no word holds three clouds then: every boundary word of a whole cloud is tallied in shared memory)
+                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb;
                 // The TNF kernel is bound by shared-memory atomics, the look-up sweep below by L1 gathers: with a few CTAs per SM
                 // on the second stream it runs NEXT TO the sweep instead of before it.
                 const bool side = ctx->tnf_overlap > 0;

@@ -45,7 +45,6 @@ struct FeatParams {
     const int32_t* row_lb;      // n_groups: rows emitted before cloud g
     int32_t tnf_k, vs, td;
     int32_t tnf_slots;          // tnf.cuh: cloud slots with block-private bins
-    int32_t tnf_store;          // tnf.cuh: rows of clouds that lie wholly inside a tile are STORED, not reduced (needs clouds >= 64 bytes)
     uint32_t ws, clamp;         // clamp = min(ws * vs, 2^32-1): counts >= clamp fall outside the histogram
     uint32_t magic;             // ceil(2^32 / ws) when use_magic
     int32_t use_magic;

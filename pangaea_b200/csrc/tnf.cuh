@@ -34,9 +34,7 @@ tnf_kernel(const FeatParams P)
     const int nb = 1 << (2 * tk);                                  // raw bins per slot
     const int n_slots = P.tnf_slots;                               // host: as many as fit (api.cu)
     uint32_t* bins = smem;                                         // [n_slots][nb] + 1 dummy
-    uint32_t* cols = bins + n_slots * nb + 1;                      // td canonical columns: a whole cloud's row is folded here and stored
-    uint16_t* lut_s = reinterpret_cast<uint16_t*>(cols + P.td);
-    for (int i = threadIdx.x; i < P.td; i += blockDim.x) cols[i] = 0u;
+    uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + n_slots * nb + 1);
     for (int i = threadIdx.x; i < n_slots * nb + 1; i += blockDim.x) bins[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) lut_s[i] = P.lut[i];
     __syncthreads();
@@ -141,25 +139,9 @@ tnf_kernel(const FeatParams P)
                 if (row < 0) continue;
                 uint32_t* src = bins + s * nb;
                 uint32_t* dst = P.tnf + (int64_t)row * P.td;
-                // A cloud that lies wholly inside this tile, boundary words included (they were tallied in shared memory when the
-                // neighbour's slot exists: s + 1 < n_slots), has no other writer: its row is folded to the canonical columns
-                // and STORED, 4 * td contiguous bytes, instead of ~200 REDs into a row that is not in L2 (one cloud per read
-                // pair: 60 G REDs per 300 M pairs).  Clouds that continue in another tile / CTA add up with REDs in the zeroed matrix.
-                const bool whole = P.tnf_store && s + 1u < (uint32_t)n_slots && __ldg(P.gstart + g_lo + s) >= tile * 32 &&
-                                   __ldg(P.gstart + g_lo + s + 1) <= tile_end * 32;
-                if (whole) { // (uniform for the block)
-                    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-                        const uint32_t v = src[b];
-                        if (v) { atomicAdd(cols + lut_s[b], v); src[b] = 0u; }
-                    }
-                    __syncthreads();
-                    for (int c2 = threadIdx.x; c2 < P.td; c2 += blockDim.x) { dst[c2] = cols[c2]; cols[c2] = 0u; }
-                    __syncthreads();
-                } else {
-                    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-                        const uint32_t v = src[b];
-                        if (v) { atomicAdd(dst + lut_s[b], v); src[b] = 0u; }
-                    }
+                for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                    const uint32_t v = src[b];
+                    if (v) { atomicAdd(dst + lut_s[b], v); src[b] = 0u; }
                 }
             }
             __syncthreads();

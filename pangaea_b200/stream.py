@@ -91,9 +91,17 @@ class DeviceIngest:
 
         fs_path = _lib.os.fsencode(self.path)
 
+        debug = _lib.os.environ.get("PG_INGEST_DEBUG") == "1"
+
         def stage(k, lo, hi):  # file bytes [lo, hi) -> views[k][slack : slack + hi - lo]: pread on all cores, no mapping
+            import time
+
+            t0 = time.perf_counter()
             if hi > lo and L.pg_parallel_pread(fs_path, lo, hi - lo, state["views"][k][slack:].ctypes.data) != 0:
                 state["error"] = _lib.PgError(-4, f"cannot read {self.path!r}")  # (may run on the staging thread)
+            if debug:
+                dt = time.perf_counter() - t0
+                print(f"[ingest] staged {hi - lo} bytes in {1e3 * dt:.1f} ms ({(hi - lo) / 1e9 / max(dt, 1e-9):.1f} GB/s)", file=_lib.sys.stderr, flush=True)
 
         alloc()
         last, rt = b"", 0
