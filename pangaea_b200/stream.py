@@ -63,9 +63,12 @@ class _Prefetch:
 
 class DeviceIngest:
     """Batches of a plain-text INTERLEAVED FASTQ parsed ON THE DEVICE (csrc/ingest.cuh, pg_ingest_text): the host only
-    moves raw file bytes into a pinned staging buffer (all cores) and from there over PCIe; the line index, getBarcode,
-    the cloud flags and the 2-bit pack happen in HBM.  While the GPU works on window w the host stages window w + 1; the
-    part of w behind its last cloud flush (or an incomplete record) is put in front of it.
+    moves raw file bytes; the line index, getBarcode, the cloud flags and the 2-bit pack happen in HBM.
+
+    Three stages run concurrently on consecutive windows of the file: (1) `pread` by all host cores into one of two pinned
+    buffers (~38 GB/s on the 16-core box), (2) the H2D copy of the window on a copy stream (PCIe), (3) the device parse and
+    whatever the consumer does with the batch (the count pass).  The part of a window behind its last cloud flush - or an
+    incomplete record - is moved, device to device, in front of the next window's bytes.
 
     Iterating yields (Batch, keep uint8[], labels list[str], is_last_batch)."""
 
@@ -73,6 +76,8 @@ class DeviceIngest:
         self.ctx, self.path, self.window, self.slack = ctx, path, int(window_bytes), int(slack_bytes)
 
     def __iter__(self):
+        import time
+
         import torch
 
         ctx = self.ctx
@@ -82,68 +87,88 @@ class DeviceIngest:
             yield batch, keep, labels, True
             return
         L = _lib.lib()
-        window, slack = self.window, self.slack
-        state = {}
-
-        def alloc():
-            state["bufs"] = [torch.empty(slack + window, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-            state["views"] = [b.numpy() for b in state["bufs"]]
-
+        W, slack = self.window, self.slack
+        n_win = (n + W - 1) // W
+        dev_name = f"cuda:{ctx.params.device}"
+        host = [torch.empty(W, dtype=torch.uint8, pin_memory=True) for _ in range(min(2, n_win))]
+        dev = [torch.empty(slack + W, dtype=torch.uint8, device=dev_name) for _ in range(min(2, n_win))]
+        copy_stream = torch.cuda.Stream(device=dev_name)
         fs_path = _lib.os.fsencode(self.path)
-
         debug = _lib.os.environ.get("PG_INGEST_DEBUG") == "1"
+        issued = [threading.Event() for _ in range(n_win)]   # the H2D of window w is queued (h2d[w] is its CUDA event)
+        parsed = [threading.Event() for _ in range(n_win)]   # the parse of window w has returned: its device buffer may be refilled
+        h2d = [None] * n_win
+        failure = []
 
-        def stage(k, lo, hi):  # file bytes [lo, hi) -> views[k][slack : slack + hi - lo]: pread on all cores, no mapping
-            import time
+        def producer():
+            try:
+                for w in range(n_win):
+                    k = w % 2
+                    if w >= 2:
+                        h2d[w - 2].synchronize()   # the pinned buffer is read no more
+                        parsed[w - 2].wait()       # the device buffer is parsed (and its tail moved on)
+                        if failure:
+                            return
+                    lo, hi = w * W, min(n, (w + 1) * W)
+                    t0 = time.perf_counter()
+                    if L.pg_parallel_pread(fs_path, lo, hi - lo, host[k].data_ptr()) != 0:
+                        raise _lib.PgError(-4, f"cannot read {self.path!r}")
+                    if debug:
+                        dt = time.perf_counter() - t0
+                        print(f"[ingest] staged {hi - lo} bytes in {1e3 * dt:.1f} ms ({(hi - lo) / 1e9 / max(dt, 1e-9):.1f} GB/s)", file=_lib.sys.stderr, flush=True)
+                    with torch.cuda.stream(copy_stream):
+                        dev[k][slack: slack + hi - lo].copy_(host[k][: hi - lo], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    h2d[w] = ev
+                    issued[w].set()
+            except BaseException as e:  # handed to the consumer
+                failure.append(e)
+                for ev in issued:
+                    ev.set()
 
-            t0 = time.perf_counter()
-            if hi > lo and L.pg_parallel_pread(fs_path, lo, hi - lo, state["views"][k][slack:].ctypes.data) != 0:
-                state["error"] = _lib.PgError(-4, f"cannot read {self.path!r}")  # (may run on the staging thread)
-            if debug:
-                dt = time.perf_counter() - t0
-                print(f"[ingest] staged {hi - lo} bytes in {1e3 * dt:.1f} ms ({(hi - lo) / 1e9 / max(dt, 1e-9):.1f} GB/s)", file=_lib.sys.stderr, flush=True)
+        feeder = threading.Thread(target=producer, daemon=True)
+        feeder.start()
+        last, rt, tail = b"", 0, 0
+        try:
+            for w in range(n_win):
+                k = w % 2
+                issued[w].wait()
+                if failure:
+                    raise failure[0]
+                h2d[w].synchronize()
+                final = w == n_win - 1
+                n_w = min(n, (w + 1) * W) - w * W
+                chunk_len = tail + n_w
+                base = dev[k].data_ptr() + slack - tail
+                batch, labels, keep, consumed, rt = ctx.ingest_text(base, last, rt, final=final, device_text=True, n_bytes=chunk_len)
+                if batch is None:  # no cloud flush inside the window: everything is carried into the next one
+                    if final:
+                        raise _lib.PgError(-5, "device ingest made no progress on the last window")
+                    consumed = 0
+                new_tail = chunk_len - consumed
+                if not final:
+                    if new_tail > slack:
+                        raise _WindowTooSmall(new_tail)
+                    if new_tail:  # device to device, in front of the next window's bytes (a different region than its H2D writes)
+                        src = dev[k][slack - tail + consumed: slack - tail + chunk_len]
+                        dev[k ^ 1][slack - new_tail: slack].copy_(src)
+                        torch.cuda.current_stream(dev_name).synchronize()
+                tail = new_tail
+                parsed[w].set()
+                if batch is not None:
+                    last = labels[-1].encode("utf-8", "surrogateescape")
+                    yield batch, keep, labels, final
+        finally:
+            if not failure:
+                failure.append(GeneratorExit())  # tells the producer to stop at its next wait
+            for ev in parsed:
+                ev.set()
+            feeder.join(timeout=60)
 
-        alloc()
-        last, rt = b"", 0
-        k, head = 0, 0                      # head: bytes in front of views[k][slack] that open the chunk (tail of the previous one)
-        lo, hi = 0, min(n, window)          # file range staged at views[k][slack:]
-        stage(k, lo, hi)
-        while True:
-            final = hi >= n
-            chunk = state["views"][k][slack - head: slack + (hi - lo)]
-            nxt, nlo, nhi = None, hi, min(n, hi + window)
-            if not final:                   # stage the next window while the GPU parses this one
-                nxt = threading.Thread(target=stage, args=(k ^ 1, nlo, nhi))
-                nxt.start()
-            batch, labels, keep, consumed, rt = ctx.ingest_text(chunk, last, rt, final=final, n_bytes=len(chunk))
-            if nxt:
-                nxt.join()
-            if "error" in state:
-                raise state["error"]
-            restart = None
-            if batch is None:               # no cloud flush inside the chunk (a cloud larger than the window): take a larger one
-                if final:
-                    raise _lib.PgError(-5, "device ingest made no progress on the last chunk")
-                window *= 2
-                restart = lo - head
-            else:
-                last = labels[-1].encode("utf-8", "surrogateescape")
-                yield batch, keep, labels, final
-                if final:
-                    return
-                tail = len(chunk) - consumed    # bytes of this chunk that the next batch starts with
-                if tail > slack:
-                    slack = 2 * tail
-                    restart = lo - head + consumed
-                else:
-                    if tail:
-                        state["views"][k ^ 1][slack - tail: slack] = chunk[consumed:]
-                    k, head, lo, hi = k ^ 1, tail, nlo, nhi
-            if restart is not None:         # rare: new buffers, staged synchronously from `restart`
-                del chunk
-                alloc()
-                k, head, lo, hi = 0, 0, restart, min(n, restart + window)
-                stage(k, lo, hi)
+
+class _WindowTooSmall(Exception):
+    """a cloud (or the run behind a window's last flush) does not fit the slack in front of a window"""
 
 
 def _size(path):
@@ -248,16 +273,30 @@ def extract_features_streaming(ctx: "_lib.Context", open_stream, clear_table=Tru
 
 
 def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 30, clear_table=True, reduce_table=None, resident_fraction=0.45,
-                                   byte_range=None):
+                                   slack_bytes=64 << 20):
     """The same two-pass flow with the DEVICE parser (DeviceIngest) as the source of batches - plain-text interleaved FASTQ
     only; gzip, paired or hostile input goes through extract_features_streaming.  Returns (names list[str], Features)."""
+    while True:
+        try:
+            return _device_ingest_two_pass(ctx, path, window_bytes, slack_bytes, clear_table, reduce_table, resident_fraction)
+        except _WindowTooSmall as e:  # rare: start over with room for the longest carried tail seen
+            slack_bytes = max(2 * slack_bytes, 2 * int(e.args[0]))
+            window_bytes = max(window_bytes, slack_bytes)
+            clear_table = True
+
+
+def _device_ingest_two_pass(ctx, path, window_bytes, slack_bytes, clear_table, reduce_table, resident_fraction):
     if clear_table:
         ctx.table_clear()
     _, total = ctx.mem_info()
     budget = int(total * resident_fraction)
+    import time
+
+    debug = _lib.os.environ.get("PG_INGEST_DEBUG") == "1"
+    t_start = time.perf_counter()
     held, resident, keep_resident = [], 0, True
     keep_part = keep_partitions(ctx, 0.45 * _size(path))  # (sequence lines are ~40 % of a FASTQ file's bytes)
-    for batch, keep, labels, is_last in DeviceIngest(ctx, path, window_bytes):
+    for batch, keep, labels, is_last in DeviceIngest(ctx, path, window_bytes, slack_bytes):
         single = is_last and not held
         ctx.count(batch, keep_partition=single or keep_part)
         n_reads, n_bytes = batch.shape()
@@ -277,6 +316,10 @@ def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 
         held.append([batch, keep, labels])
     if reduce_table:
         reduce_table()
+    if debug:
+        ctx.synchronize()
+        print(f"[ingest] pass 1 (stage, copy, parse, count; {len(held)} batches): {1e3 * (time.perf_counter() - t_start):.1f} ms", file=_lib.sys.stderr, flush=True)
+        t_start = time.perf_counter()
     names, parts = [], []
     if keep_resident:
         for b, keep, labels in held:
@@ -284,8 +327,11 @@ def extract_features_device_ingest(ctx: "_lib.Context", path, window_bytes=1 << 
             names += [labels[g] for g in f.row_groups().tolist()]
             b.free()
             parts.append(f)
+        if debug:
+            ctx.synchronize()
+            print(f"[ingest] pass 2 (featurize, row labels): {1e3 * (time.perf_counter() - t_start):.1f} ms", file=_lib.sys.stderr, flush=True)
     else:
-        for i, (b, keep, labels, _) in enumerate(DeviceIngest(ctx, path, window_bytes)):
+        for i, (b, keep, labels, _) in enumerate(DeviceIngest(ctx, path, window_bytes, slack_bytes)):
             if len(keep) != len(held[i][1]):
                 raise _lib.PgError(-5, "the input changed between the two passes")
             f = ctx.featurize(b, keep)
