@@ -161,3 +161,37 @@ def test_sorted_file_then_features_equal_oracle(tmp_path, oracle):
     g_names, feats = stream.extract_features_device_ingest(ctx, str(tmp_path / "sorted.fq"), window_bytes=500_000)
     g_abd, g_tnf = feats.raw()
     assert g_names == list(names) and len(names) > 50 and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+
+
+def test_device_parse_property_random_text(tmp_path):
+    """hypothesis: on arbitrary hostile text - blank lines, '\\r', headers with or without BX / '#', records cut anywhere, no final
+    newline - the device parser (windows of random size) returns exactly what the host reader returns."""
+    from hypothesis import given, settings, strategies as st
+
+    header = st.one_of(
+        st.builds(lambda n, bc: b"@r%d BX:Z:%s-1" % (n, bc), st.integers(0, 99), st.sampled_from([b"AAAA", b"AAAC", b"CC", b"", b"GG-TT"])),
+        st.builds(lambda n, bc, m: b"@r%d#%s/%d" % (n, bc, m), st.integers(0, 99), st.sampled_from([b"1_1_1", b"0_0_0", b"2_2_2", b""]), st.integers(1, 2)),
+        st.sampled_from([b"@plain", b"", b"@x\tBX:Z:AAAA", b"@y BX:Z:", b"# /", b"@z\r", b"BX:Z", b"@q BX:Z:A#B/1"]))
+    seq = st.one_of(st.text(alphabet="ACGTNacgt", min_size=0, max_size=40).map(str.encode), st.sampled_from([b"", b"ACGT\r", b"@ACGT", b"+"]))
+    line = st.one_of(header, seq, st.sampled_from([b"+", b"IIII", b"", b"????"]))
+    record = st.tuples(header, seq, st.just(b"+"), seq).map(lambda t: list(t))
+    text = st.one_of(st.lists(record, max_size=40).map(lambda rs: [l for r in rs for l in r]), st.lists(line, max_size=80))
+    ctx = _lib.Context(table_mode=_lib.PG_TABLE_NONE)
+    counter = [0]
+
+    @settings(max_examples=150, deadline=None)
+    @given(lines=text, final_newline=st.booleans(), window=st.sampled_from([40, 150, 600, 10 ** 6]))
+    def check(lines, final_newline, window):
+        counter[0] += 1
+        data = b"\n".join(lines) + (b"\n" if final_newline and lines else b"")
+        path = str(tmp_path / f"p{counter[0] % 4}.fq")
+        open(path, "wb").write(data)
+        want = _host(path)
+        chunks = _device_chunks(ctx, data, window)
+        seq_, off, flag, labels = _concat(chunks)
+        live = np.diff(off) > 0
+        assert np.array_equal(seq_, want[0]), data
+        assert np.array_equal(np.diff(off)[live], np.diff(want[1])) and np.array_equal(flag[live], want[2]) and not flag[~live].any(), data
+        assert labels == want[4], data
+
+    check()
