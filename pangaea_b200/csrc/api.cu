@@ -144,12 +144,27 @@ struct pg_features {
 };
 
 static thread_local std::string g_err;
+static thread_local bool g_err_caught = false; // the newest message is in g_err only (caught(): no ctx at hand)
 
 static int fail(pg_ctx* c, int code, const std::string& msg)
 {
     g_err = msg;
+    g_err_caught = false;
     if (c) c->err = msg;
     return code;
+}
+
+// No C++ exception crosses the C-ABI: every int-returning entry point is a function-try-block that ends here
+// (std::bad_alloc from the host-side vectors / strings is the realistic one).
+static int caught(const char* fn) noexcept
+{
+    g_err_caught = true;
+    try {
+        try { throw; }
+        catch (const std::bad_alloc&) { g_err = std::string(fn) + ": out of host memory"; return PG_ERR_CUDA; }
+        catch (const std::exception& e) { g_err = std::string(fn) + ": " + e.what(); return PG_ERR_STATE; }
+        catch (...) { g_err = std::string(fn) + ": unknown C++ exception"; return PG_ERR_STATE; }
+    } catch (...) { return PG_ERR_STATE; } // (even the message could not be built)
 }
 
 #define CK(call)                                                                                       \
@@ -276,11 +291,11 @@ static int build_tnf_lut(int tk, std::vector<uint16_t>* lut)
 extern "C" int pg_tnf_dim(int tnf_k) { return (tnf_k < 1 || tnf_k > 6) ? -1 : build_tnf_lut(tnf_k, nullptr); }
 
 extern "C" int pg_device_count(void)
-{
+try {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
-}
+} catch (...) { return caught("pg_device_count"); }
 
 extern "C" void pg_default_params(pg_params* p)
 {
@@ -296,7 +311,7 @@ extern "C" void pg_default_params(pg_params* p)
     p->table_capacity = 0;
 }
 
-extern "C" const char* pg_last_error(const pg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+extern "C" const char* pg_last_error(const pg_ctx* ctx) { return (ctx && !g_err_caught) ? ctx->err.c_str() : g_err.c_str(); }
 
 static TableView view(pg_ctx* c)
 {
@@ -317,7 +332,7 @@ static int alloc_hash(pg_ctx* ctx, uint64_t slots)
 }
 
 extern "C" int pg_create(const pg_params* p, pg_ctx** out)
-{
+try {
     pg_ctx* ctx = nullptr;
     if (!p || !out) return fail(nullptr, PG_ERR_INVALID, "pg_create: null argument");
     *out = nullptr;
@@ -419,7 +434,7 @@ extern "C" int pg_create(const pg_params* p, pg_ctx** out)
 #undef CKC
     *out = ctx;
     return PG_OK;
-}
+} catch (...) { return caught("pg_create"); }
 
 extern "C" void pg_destroy(pg_ctx* ctx)
 {
@@ -442,19 +457,19 @@ extern "C" void pg_destroy(pg_ctx* ctx)
 }
 
 extern "C" int pg_synchronize(pg_ctx* ctx)
-{
+try {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     CK(cudaSetDevice(ctx->p.device));
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_synchronize"); }
 
 extern "C" void* pg_stream(pg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 static size_t available_bytes(pg_ctx* ctx);
 
 extern "C" int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes)
-{
+try {
     if (!ctx || !free_bytes || !total_bytes) return fail(ctx, PG_ERR_INVALID, "pg_mem_info: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     size_t f = 0, t = 0;
@@ -464,23 +479,23 @@ extern "C" int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_byte
     *free_bytes = (int64_t)(available_bytes(ctx) + ctx->big.free_bytes + idle);
     *total_bytes = (int64_t)t;
     return PG_OK;
-}
+} catch (...) { return caught("pg_mem_info"); }
 
 // ---------------------------------------------------------------------------
 // timing
 // ---------------------------------------------------------------------------
 extern "C" int pg_timing_reset(pg_ctx* ctx)
-{
+try {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& s : ctx->spans) { ctx->pool.push_back(s.a); ctx->pool.push_back(s.b); }
     ctx->spans.clear();
     memset(ctx->launches, 0, sizeof(ctx->launches));
     return PG_OK;
-}
+} catch (...) { return caught("pg_timing_reset"); }
 
 extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* launches_out)
-{
+try {
     if (!ctx || which < 0 || which >= T_SLOTS) return fail(ctx, PG_ERR_INVALID, "pg_timing_get: bad argument");
     CK(cudaStreamSynchronize(ctx->stream));
     double ms = 0;
@@ -496,7 +511,7 @@ extern "C" int pg_timing_get(pg_ctx* ctx, int which, double* ms_out, int64_t* la
     if (ms_out) *ms_out = ms;
     if (launches_out) *launches_out = n;
     return PG_OK;
-}
+} catch (...) { return caught("pg_timing_get"); }
 
 // ---------------------------------------------------------------------------
 // batches
@@ -567,7 +582,7 @@ static int check_host_batch(pg_ctx* ctx, const pg_reads* h)
 }
 
 extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
-{
+try {
     if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
     *out = nullptr;
     int rc = check_host_batch(ctx, h);
@@ -589,10 +604,10 @@ extern "C" int pg_batch_upload(pg_ctx* ctx, const pg_reads* h, pg_batch** out)
     if (rc) { pg_batch_free(ctx, b); return rc; }
     *out = b;
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_upload"); }
 
 extern "C" int pg_batch_adopt(pg_ctx* ctx, const pg_reads* d, pg_batch** out)
-{
+try {
     int rc = check_reads(ctx, d);
     if (rc) return rc;
     if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
@@ -611,7 +626,7 @@ extern "C" int pg_batch_adopt(pg_ctx* ctx, const pg_reads* d, pg_batch** out)
     if (rc) { pg_batch_free(ctx, b); return rc; }
     *out = b;
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_adopt"); }
 
 extern "C" void pg_batch_shape(const pg_batch* b, int64_t* n_reads, int64_t* n_bytes)
 {
@@ -620,7 +635,7 @@ extern "C" void pg_batch_shape(const pg_batch* b, int64_t* n_reads, int64_t* n_b
 }
 
 extern "C" int pg_batch_download(pg_ctx* ctx, const pg_batch* b, uint8_t* seq_out, int64_t* read_off_out, uint8_t* read_flag_out)
-{
+try {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "pg_batch_download: bad argument");
     if (seq_out && !b->seq) return fail(ctx, PG_ERR_STATE, "pg_batch_download: the batch was compacted, its bases are gone");
     CK(cudaSetDevice(ctx->p.device));
@@ -629,7 +644,7 @@ extern "C" int pg_batch_download(pg_ctx* ctx, const pg_batch* b, uint8_t* seq_ou
     if (read_flag_out && b->n_reads) CK(cudaMemcpyAsync(read_flag_out, b->read_flag, (size_t)b->n_reads, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_download"); }
 
 static void free_stash(pg_ctx* ctx, pg_batch* b)
 {
@@ -660,7 +675,7 @@ extern "C" void pg_batch_free(pg_ctx* ctx, pg_batch* b)
 static int table_ready(pg_ctx* ctx);
 
 extern "C" int pg_table_clear(pg_ctx* ctx)
-{
+try {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
@@ -671,7 +686,7 @@ extern "C" int pg_table_clear(pg_ctx* ctx)
     ctx->counted = false;
     ctx->zero_markers = false;
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_clear"); }
 
 static int ensure_table(pg_ctx* ctx, int64_t hint_windows)
 {
@@ -940,7 +955,7 @@ static int count_bucketed(pg_ctx* ctx, pg_batch* b, bool keep)
 extern "C" int pg_count(pg_ctx* ctx, pg_batch* b) { return pg_count2(ctx, b, 1); }
 
 extern "C" int pg_count2(pg_ctx* ctx, pg_batch* b, int keep_partition)
-{
+try {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
@@ -965,10 +980,10 @@ extern "C" int pg_count2(pg_ctx* ctx, pg_batch* b, int keep_partition)
     CK(cudaGetLastError());
     ctx->counted = true;
     return check_overflow(ctx);
-}
+} catch (...) { return caught("pg_count2"); }
 
 extern "C" int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* counts, int64_t n)
-{
+try {
     if (!ctx || (n > 0 && (!keys || !counts)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_set: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
@@ -1003,10 +1018,10 @@ extern "C" int pg_table_set(pg_ctx* ctx, const uint64_t* keys, const uint32_t* c
     CK(cudaStreamSynchronize(ctx->stream)); // hk/hc are about to go out of scope
     dfree(ctx, dk); dfree(ctx, dc);
     return check_overflow(ctx);
-}
+} catch (...) { return caught("pg_table_set"); }
 
 extern "C" int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* out, int64_t n)
-{
+try {
     if (!ctx || (n > 0 && (!keys || !out)) || n < 0) return fail(ctx, PG_ERR_INVALID, "pg_table_get: bad argument");
     if (!n) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -1021,10 +1036,10 @@ extern "C" int pg_table_get(pg_ctx* ctx, const uint64_t* keys, uint32_t* out, in
     CK(cudaStreamSynchronize(ctx->stream));
     dfree(ctx, dk); dfree(ctx, dc);
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_get"); }
 
 extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
-{
+try {
     if (!ctx || !n_distinct) return fail(ctx, PG_ERR_INVALID, "pg_table_size: bad argument");
     *n_distinct = 0;
     if (!ctx->have_table()) return PG_OK;
@@ -1038,10 +1053,10 @@ extern "C" int pg_table_size(pg_ctx* ctx, int64_t* n_distinct)
     CK(cudaStreamSynchronize(ctx->stream));
     *n_distinct = ctx->h_pin[0];
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_size"); }
 
 extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts_out, int64_t cap, int64_t* n_out)
-{
+try {
     if (!ctx || !keys_out || !counts_out || cap < 0 || !n_out) return fail(ctx, PG_ERR_INVALID, "pg_table_export: bad argument");
     *n_out = 0;
     if (!ctx->have_table() || !cap) return PG_OK;
@@ -1068,7 +1083,7 @@ extern "C" int pg_table_export(pg_ctx* ctx, uint64_t* keys_out, uint32_t* counts
     *n_out = n;
     if (ctx->h_pin[0] > cap) return fail(ctx, PG_ERR_INVALID, "pg_table_export: buffer too small");
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_export"); }
 
 // order the ctx stream after a pending external write of the table; called by everything that touches the table
 static int table_ready(pg_ctx* ctx)
@@ -1082,24 +1097,24 @@ static int table_ready(pg_ctx* ctx)
 }
 
 extern "C" int pg_table_wait_event(pg_ctx* ctx, void* cuda_event)
-{
+try {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     ctx->table_event = (cudaEvent_t)cuda_event;
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_wait_event"); }
 
 extern "C" int pg_table_dense_view(pg_ctx* ctx, void** dev_ptr, int64_t* n_entries)
-{
+try {
     if (!ctx || !dev_ptr || !n_entries) return fail(ctx, PG_ERR_INVALID, "pg_table_dense_view: bad argument");
     if (ctx->mode != kDense) return fail(ctx, PG_ERR_STATE, "pg_table_dense_view: table is not dense");
     *dev_ptr = ctx->counts;
     *n_entries = (int64_t)ctx->n_slots;
     ctx->counted = true; // a caller that sums tables across ranks owns the contents
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_dense_view"); }
 
 extern "C" int pg_table_clamp(pg_ctx* ctx, uint32_t max_count)
-{
+try {
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
     if (ctx->mode != kDense || !ctx->counts) return fail(ctx, PG_ERR_STATE, "pg_table_clamp: table is not dense");
     if (ctx->zero_markers) return fail(ctx, PG_ERR_STATE, "pg_table_clamp: the table holds zero-count markers from pg_table_set");
@@ -1109,7 +1124,7 @@ extern "C" int pg_table_clamp(pg_ctx* ctx, uint32_t max_count)
     table_saturate_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts, ctx->n_slots, max_count, nullptr);
     CK(cudaGetLastError());
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_clamp"); }
 
 // ---------------------------------------------------------------------------
 // grouping + featurize
@@ -1198,12 +1213,12 @@ static int group_stage_a(pg_ctx* ctx, pg_batch* b, bool want_wg, bool packed)
 }
 
 extern "C" int pg_featurize(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
-{
+try {
     return pg_featurize2(ctx, b, group_keep, n_groups, 0, out);
-}
+} catch (...) { return caught("pg_featurize"); }
 
 extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep, int64_t n_groups, int flags, pg_features** out)
-{
+try {
     if (!ctx || !b || !out || n_groups < 1 || !group_keep) return fail(ctx, PG_ERR_INVALID, "pg_featurize: bad argument");
     *out = nullptr;
     const bool no_abd = (flags & PG_FEAT_NO_ABUNDANCE) != 0;
@@ -1298,7 +1313,8 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
                 const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
                 const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
                 P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
-                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb;
+                const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb
+                                      + (P.tnf_k <= kTnfFoldMaxK ? ((size_t)(kTnfThreads / 32) * P.td + 2) * sizeof(uint32_t) : 0);
                 // The TNF kernel is bound by shared-memory atomics, the look-up sweep below by L1 gathers: with a few CTAs per SM
                 // on the second stream it runs NEXT TO the sweep instead of before it.
                 const bool side = ctx->tnf_overlap > 0;
@@ -1435,7 +1451,7 @@ extern "C" int pg_featurize2(pg_ctx* ctx, pg_batch* b, const uint8_t* group_keep
 #undef CKF
     *out = f;
     return PG_OK;
-}
+} catch (...) { return caught("pg_featurize2"); }
 
 // With a live ctx the buffers go back to the pool in stream order (no device-wide sync, and
 // the next step's allocations reuse them); the DLPack deleter has no ctx and frees synchronously.
@@ -1465,7 +1481,7 @@ extern "C" int32_t pg_features_abd_dim(const pg_features* f) { return f ? f->vs 
 extern "C" int32_t pg_features_tnf_dim(const pg_features* f) { return f ? f->td : -1; }
 
 extern "C" int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t* groups_out)
-{
+try {
     if (!ctx || !f || (f->rows && !groups_out)) return fail(ctx, PG_ERR_INVALID, "pg_features_row_groups: bad argument");
     if (!f->rows) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -1474,23 +1490,23 @@ extern "C" int pg_features_row_groups(pg_ctx* ctx, const pg_features* f, int64_t
     CK(cudaStreamSynchronize(ctx->stream));
     for (int64_t i = 0; i < f->rows; ++i) groups_out[i] = tmp[i];
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_row_groups"); }
 
 extern "C" int pg_features_copy_raw(pg_ctx* ctx, const pg_features* f, int32_t* abd_out, int32_t* tnf_out)
-{
+try {
     if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_features_copy_raw: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     if (abd_out && f->rows) CK(cudaMemcpyAsync(abd_out, f->abd_raw, (size_t)f->rows * f->vs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (tnf_out && f->rows) CK(cudaMemcpyAsync(tnf_out, f->tnf_raw, (size_t)f->rows * f->td * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_copy_raw"); }
 
 // ---------------------------------------------------------------------------
 // Data.__init__
 // ---------------------------------------------------------------------------
 extern "C" int pg_normalize(pg_ctx* ctx, pg_features* f)
-{
+try {
     if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_normalize: bad argument");
     if (f->normalized) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -1499,23 +1515,32 @@ extern "C" int pg_normalize(pg_ctx* ctx, pg_features* f)
     CK(dmalloc(ctx, &f->weights, (size_t)f->rows));
     if (f->rows) {
         Timed t(ctx, T_NORM, 2);
-        if (f->rows >= (1 << 20)) { // millions of rows: four of them per warp in flight
-            const int grid = grid_for(f->rows * 8, 256, ctx->sm_count * 8);
-            normalize_rows_kernel<8><<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
-            normalize_rows_kernel<8><<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
-        } else {
-            const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
-            normalize_rows_kernel<32><<<grid, 256, 0, ctx->stream>>>(f->abd_raw, f->rows, f->vs, f->abd, f->weights, 1);
-            normalize_rows_kernel<32><<<grid, 256, 0, ctx->stream>>>(f->tnf_raw, f->rows, f->td, f->tnf, nullptr, 1);
-        }
+        auto launch = [&](const uint32_t* raw, int dim, float* out, double* w) {
+            if (dim % 4 == 0 && dim <= 512) { // the production shapes: one warp per row, 16-byte vectors, one read
+                const int nvec = dim / 4, vpl = (nvec + 31) / 32;
+                const int grid = grid_for(f->rows * 32, 256, ctx->sm_count * 8);
+                const uint4* r4 = reinterpret_cast<const uint4*>(raw);
+                float4* o4 = reinterpret_cast<float4*>(out);
+                if (vpl == 1) normalize_rows_vec_kernel<1><<<grid, 256, 0, ctx->stream>>>(r4, f->rows, nvec, o4, w, 1);
+                else if (vpl == 2) normalize_rows_vec_kernel<2><<<grid, 256, 0, ctx->stream>>>(r4, f->rows, nvec, o4, w, 1);
+                else if (vpl == 3) normalize_rows_vec_kernel<3><<<grid, 256, 0, ctx->stream>>>(r4, f->rows, nvec, o4, w, 1);
+                else normalize_rows_vec_kernel<4><<<grid, 256, 0, ctx->stream>>>(r4, f->rows, nvec, o4, w, 1);
+            } else if (f->rows >= (1 << 20)) { // millions of rows: four of them per warp in flight
+                normalize_rows_kernel<8><<<grid_for(f->rows * 8, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(raw, f->rows, dim, out, w, 1);
+            } else {
+                normalize_rows_kernel<32><<<grid_for(f->rows * 32, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(raw, f->rows, dim, out, w, 1);
+            }
+        };
+        launch(f->abd_raw, f->vs, f->abd, f->weights);
+        launch(f->tnf_raw, f->td, f->tnf, nullptr);
     }
     CK(cudaGetLastError());
     f->normalized = true;
     return PG_OK;
-}
+} catch (...) { return caught("pg_normalize"); }
 
 extern "C" int pg_features_from_raw(pg_ctx* ctx, const uint32_t* abd, const uint32_t* tnf, int64_t rows, int32_t abd_dim, int32_t tnf_dim, pg_features** out)
-{
+try {
     if (!ctx || !out || rows < 0 || abd_dim < 1 || tnf_dim < 1 || (rows && (!abd || !tnf))) return fail(ctx, PG_ERR_INVALID, "pg_features_from_raw: bad argument");
     *out = nullptr;
     CK(cudaSetDevice(ctx->p.device));
@@ -1531,10 +1556,10 @@ extern "C" int pg_features_from_raw(pg_ctx* ctx, const uint32_t* abd, const uint
     if (e != cudaSuccess) { pg_features_free(ctx, f); return fail(ctx, PG_ERR_CUDA, std::string("pg_features_from_raw: ") + cudaGetErrorString(e)); }
     *out = f;
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_from_raw"); }
 
 extern "C" int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, float* abd_out, float* tnf_out, double* weights_out)
-{
+try {
     if (!ctx || !f) return fail(ctx, PG_ERR_INVALID, "pg_features_copy_normalized: bad argument");
     if (!f->normalized) return fail(ctx, PG_ERR_STATE, "call pg_normalize first");
     CK(cudaSetDevice(ctx->p.device));
@@ -1543,7 +1568,7 @@ extern "C" int pg_features_copy_normalized(pg_ctx* ctx, const pg_features* f, fl
     if (weights_out && f->rows) CK(cudaMemcpyAsync(weights_out, f->weights, (size_t)f->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_copy_normalized"); }
 
 extern "C" void* pg_features_device_ptr(const pg_features* f, int which)
 {
@@ -1670,7 +1695,7 @@ static int upload_and_count_pipelined(pg_ctx* ctx, const pg_reads* h, pg_batch**
 
 // upload + count of one batch of a stream; the table is NOT cleared (batches add up)
 extern "C" int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep_partition, pg_batch** out)
-{
+try {
     if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
     *out = nullptr;
     if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
@@ -1692,10 +1717,10 @@ extern "C" int pg_batch_upload_count(pg_ctx* ctx, const pg_reads* host, int keep
     }
     *out = b;
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_upload_count"); }
 
 extern "C" int pg_batch_compact(pg_ctx* ctx, pg_batch* b)
-{
+try {
     if (!ctx || !b) return fail(ctx, PG_ERR_INVALID, "null argument");
     CK(cudaSetDevice(ctx->p.device));
     if (b->owns) { dfree(ctx, b->seq); dfree(ctx, b->qual); }
@@ -1713,10 +1738,10 @@ extern "C" int pg_batch_compact(pg_ctx* ctx, pg_batch* b)
     }
     b->seq = b->qual = nullptr; // (a kept partition stays: pg_count2's keep_partition decides about it)
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_compact"); }
 
 extern "C" int pg_features_concat(pg_ctx* ctx, pg_features* const* parts, int32_t n_parts, pg_features** out)
-{
+try {
     if (!ctx || !out || n_parts < 0 || (n_parts && !parts)) return fail(ctx, PG_ERR_INVALID, "pg_features_concat: bad argument");
     *out = nullptr;
     CK(cudaSetDevice(ctx->p.device));
@@ -1745,10 +1770,10 @@ extern "C" int pg_features_concat(pg_ctx* ctx, pg_features* const* parts, int32_
     if (e != cudaSuccess) { pg_features_free(ctx, f); return fail(ctx, PG_ERR_CUDA, std::string("pg_features_concat: ") + cudaGetErrorString(e)); }
     *out = f;
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_concat"); }
 
 extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint8_t* group_keep, int64_t n_groups, pg_features** out)
-{
+try {
     if (!out) return fail(ctx, PG_ERR_INVALID, "null out");
     *out = nullptr;
     int rc = pg_table_clear(ctx);
@@ -1770,7 +1795,7 @@ extern "C" int pg_extract_features(pg_ctx* ctx, const pg_reads* host, const uint
     if (rc) { if (f) pg_features_free(ctx, f); return rc; }
     *out = f;
     return PG_OK;
-}
+} catch (...) { return caught("pg_extract_features"); }
 
 // ---------------------------------------------------------------------------
 // synthetic reads (bench input)
@@ -1779,7 +1804,7 @@ extern "C" int pg_synth_generate2(pg_ctx* ctx, int64_t n_pairs, int32_t read_len
                                   const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
                                   double n_rate, uint64_t seed, int64_t bc_base, int64_t pair_base, uint8_t* d_seq, int64_t* d_read_off,
                                   uint8_t* d_read_flag)
-{
+try {
     if (!ctx || n_pairs < 0 || read_len < 1 || n_barcodes < 1 || !d_bc_start || !d_bc_genome || !d_seq || !d_read_off || !d_read_flag)
         return fail(ctx, PG_ERR_INVALID, "pg_synth_generate: bad argument");
     if (insert < read_len || frag_len < insert || genome_len < frag_len) return fail(ctx, PG_ERR_INVALID, "need read_len <= insert <= frag_len <= genome_len");
@@ -1795,14 +1820,14 @@ extern "C" int pg_synth_generate2(pg_ctx* ctx, int64_t n_pairs, int32_t read_len
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_synth_generate2"); }
 
 extern "C" int pg_synth_generate(pg_ctx* ctx, int64_t n_pairs, int32_t read_len, int64_t n_barcodes, const int64_t* d_bc_start,
                                  const int32_t* d_bc_genome, int64_t genome_len, int32_t frag_len, int32_t insert, double sub_rate,
                                  double n_rate, uint64_t seed, uint8_t* d_seq, int64_t* d_read_off, uint8_t* d_read_flag)
-{
+try {
     return pg_synth_generate2(ctx, n_pairs, read_len, n_barcodes, d_bc_start, d_bc_genome, genome_len, frag_len, insert, sub_rate, n_rate, seed, 0, 0,
                               d_seq, d_read_off, d_read_flag);
-}
+} catch (...) { return caught("pg_synth_generate"); }
 
 #include "ingest_api.cuh"

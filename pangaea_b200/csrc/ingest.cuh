@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kScan64Threads) scan64_tiles_kernel(long long*
 }
 
 // out[i] = exclusive prefix of in[0..i); out may alias in; out[n] is NOT written (the total goes to total_out of the tiles kernel)
-__global__ void __launch_bounds__(kScan64Threads) scan64_apply_kernel(const long long* __restrict__ in, int64_t n, const long long* __restrict__ tile_off,
-                                                                      long long* __restrict__ out)
+__global__ void __launch_bounds__(kScan64Threads) scan64_apply_kernel(const long long* in, int64_t n, const long long* __restrict__ tile_off,
+                                                                      long long* out) // (in / out unqualified: they may alias)
 {
     const int64_t base = (int64_t)blockIdx.x * kScan64Tile + (int64_t)threadIdx.x * kScan64Items;
     long long v[kScan64Items], c = 0;

@@ -79,7 +79,7 @@ extern "C" int64_t pg_ingest_group_labels(const pg_ingest* g, char* buf, int64_t
 // text (host or device memory) -> a packed pg_batch + the labels of its clouds.  See include/pangaea_b200.h.
 extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, int flags, const char* last_barcode, int64_t last_len,
                               int32_t* read_type_io, int64_t* consumed_out, pg_batch** batch_out, pg_ingest** info_out)
-{
+try {
     if (!ctx || !batch_out || !info_out || !consumed_out || !read_type_io || n_bytes < 0 || (n_bytes && !text) || last_len < 0 || (last_len && !last_barcode))
         return fail(ctx, PG_ERR_INVALID, "pg_ingest_text: bad argument");
     *batch_out = nullptr; *info_out = nullptr; *consumed_out = 0;
@@ -267,13 +267,13 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const void* text, int64_t n_bytes, in
 #undef CKI
     *batch_out = b; *info_out = info;
     return done(PG_OK);
-}
+} catch (...) { return caught("pg_ingest_text"); }
 
 // ---------------------------------------------------------------------------
 // barcode sort of an interleaved FASTQ held in host memory (run_pangaea:237-252)
 // ---------------------------------------------------------------------------
 extern "C" int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_in, char* out, int64_t out_cap, int64_t* n_out)
-{
+try {
     if (!ctx || n_in < 0 || (n_in && !in) || !n_out || (out_cap && !out)) return fail(ctx, PG_ERR_INVALID, "pg_fastq_sort_by_barcode: bad argument");
     *n_out = 0;
     if (n_in == 0) return PG_OK;
@@ -391,7 +391,7 @@ extern "C" int pg_fastq_sort_by_barcode(pg_ctx* ctx, const char* in, int64_t n_i
     (void)passes;
 #undef CKS
     return done(PG_OK);
-}
+} catch (...) { return caught("pg_fastq_sort_by_barcode"); }
 
 // ---------------------------------------------------------------------------
 // step-2 input pipeline: weighted sampler + batch gather (sampler.cuh)
@@ -413,7 +413,7 @@ extern "C" void pg_sampler_free(pg_ctx* ctx, pg_sampler* s)
 }
 
 extern "C" int pg_sampler_create(pg_ctx* ctx, const double* weights, int64_t n, double total, pg_sampler** out)
-{
+try {
     if (!ctx || !out || n < 1 || !weights || !(total > 0.0)) return fail(ctx, PG_ERR_INVALID, "pg_sampler_create: bad argument");
     *out = nullptr;
     CK(cudaSetDevice(ctx->p.device));
@@ -435,7 +435,7 @@ extern "C" int pg_sampler_create(pg_ctx* ctx, const double* weights, int64_t n, 
     if (e != cudaSuccess) { pg_sampler_free(ctx, s); return fail(ctx, PG_ERR_CUDA, std::string("pg_sampler_create: ") + cudaGetErrorString(e)); }
     *out = s;
     return PG_OK;
-}
+} catch (...) { return caught("pg_sampler_create"); }
 
 static int sampler_refresh_cdf(pg_ctx* ctx, pg_sampler* s)
 {
@@ -449,7 +449,7 @@ static int sampler_refresh_cdf(pg_ctx* ctx, pg_sampler* s)
 
 // with replacement: idx_out[j] = searchsorted(cdf, uniforms[j], "right").  uniforms: host memory; idx_out: device memory (m int64)
 extern "C" int pg_sampler_draw(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t* d_idx_out)
-{
+try {
     if (!ctx || !s || m < 0 || (m && (!uniforms || !d_idx_out))) return fail(ctx, PG_ERR_INVALID, "pg_sampler_draw: bad argument");
     if (!m) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -462,13 +462,13 @@ extern "C" int pg_sampler_draw(pg_ctx* ctx, pg_sampler* s, const double* uniform
     CK(cudaStreamSynchronize(ctx->stream));
     dfree(ctx, d_u);
     return PG_OK;
-}
+} catch (...) { return caught("pg_sampler_draw"); }
 
 // one round of numpy's choice(replace=False): m uniforms -> the first occurrences among the draws, appended at d_idx_out[n_found...];
 // *n_new = how many were appended.  The caller loops until it has `size` indices, drawing size - n_found fresh uniforms per round.
 extern "C" int pg_sampler_draw_unique_round(pg_ctx* ctx, pg_sampler* s, const double* uniforms, int64_t m, int64_t n_found, int64_t* d_idx_out,
                                             int64_t* n_new)
-{
+try {
     if (!ctx || !s || m < 1 || !uniforms || !d_idx_out || !n_new || n_found < 0) return fail(ctx, PG_ERR_INVALID, "pg_sampler_draw_unique_round: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     int rc = sampler_refresh_cdf(ctx, s); // the probabilities of the items found so far are zero by now
@@ -493,11 +493,11 @@ extern "C" int pg_sampler_draw_unique_round(pg_ctx* ctx, pg_sampler* s, const do
     }
     dfree(ctx, d_u); dfree(ctx, d_new); dfree(ctx, keep); dfree(ctx, rank);
     return rc;
-}
+} catch (...) { return caught("pg_sampler_draw_unique_round"); }
 
 // batch gather on the device: rows idx[0..m) of the normalised matrices (pg_normalize first) into abd_out [m, v] / tnf_out [m, td]
 extern "C" int pg_features_gather(pg_ctx* ctx, const pg_features* f, const int64_t* d_idx, int64_t m, float* d_abd_out, float* d_tnf_out)
-{
+try {
     if (!ctx || !f || m < 0 || (m && !d_idx)) return fail(ctx, PG_ERR_INVALID, "pg_features_gather: bad argument");
     if (!f->normalized) return fail(ctx, PG_ERR_STATE, "call pg_normalize first");
     if (!m) return PG_OK;
@@ -512,7 +512,7 @@ extern "C" int pg_features_gather(pg_ctx* ctx, const pg_features* f, const int64
     CK(cudaStreamSynchronize(ctx->stream));
     if (*(const uint32_t*)ctx->h_pin) return fail(ctx, PG_ERR_INVALID, "pg_features_gather: row index out of range");
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_gather"); }
 
 // ---------------------------------------------------------------------------
 // format converters and extract_reads (transform.cuh)
@@ -550,7 +550,7 @@ static int offsets_of(pg_ctx* ctx, const long long* len, int64_t n, long long* o
 
 extern "C" int pg_preprocess_stlfr(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, int library, char* out1, int64_t cap1,
                                    int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2)
-{
+try {
     if (!ctx || n1 < 0 || n2 < 0 || (n1 && !r1) || (n2 && !r2) || !n_out1 || !n_out2) return fail(ctx, PG_ERR_INVALID, "pg_preprocess_stlfr: bad argument");
     *n_out1 = *n_out2 = 0;
     CK(cudaSetDevice(ctx->p.device));
@@ -590,12 +590,12 @@ extern "C" int pg_preprocess_stlfr(pg_ctx* ctx, const char* r1, int64_t n1, cons
     CKT(cudaMemcpyAsync(out2, o2, (size_t)t2, cudaMemcpyDeviceToHost, ctx->stream));
     CKT(cudaStreamSynchronize(ctx->stream));
     return done(PG_OK);
-}
+} catch (...) { return caught("pg_preprocess_stlfr"); }
 
 extern "C" int pg_preprocess_tellseq(pg_ctx* ctx, const char* r1, int64_t n1, const char* r2, int64_t n2, const char* idx, int64_t ni, char* out1,
                                      int64_t cap1, int64_t* n_out1, char* out2, int64_t cap2, int64_t* n_out2, char* out_wl, int64_t cap_wl,
                                      int64_t* n_out_wl)
-{
+try {
     if (!ctx || n1 < 0 || n2 < 0 || ni < 0 || (n1 && !r1) || (n2 && !r2) || (ni && !idx) || !n_out1 || !n_out2 || !n_out_wl)
         return fail(ctx, PG_ERR_INVALID, "pg_preprocess_tellseq: bad argument");
     *n_out1 = *n_out2 = *n_out_wl = 0;
@@ -634,7 +634,7 @@ extern "C" int pg_preprocess_tellseq(pg_ctx* ctx, const char* r1, int64_t n1, co
     if (tw) CKT(cudaMemcpyAsync(out_wl, ow, (size_t)tw, cudaMemcpyDeviceToHost, ctx->stream));
     CKT(cudaStreamSynchronize(ctx->stream));
     return done(PG_OK);
-}
+} catch (...) { return caught("pg_preprocess_tellseq"); }
 
 // ---- extract_reads -i -------------------------------------------------------
 struct pg_extract {
@@ -661,7 +661,7 @@ extern "C" void pg_extract_close(pg_ctx* ctx, pg_extract* x)
 }
 
 extern "C" int pg_extract_open(pg_ctx* ctx, const char* text, int64_t n_bytes, pg_extract** out)
-{
+try {
     if (!ctx || !out || n_bytes < 0 || (n_bytes && !text)) return fail(ctx, PG_ERR_INVALID, "pg_extract_open: bad argument");
     *out = nullptr;
     CK(cudaSetDevice(ctx->p.device));
@@ -722,7 +722,7 @@ extern "C" int pg_extract_open(pg_ctx* ctx, const char* text, int64_t n_bytes, p
     if (rc) return bail(rc);
     *out = x;
     return PG_OK;
-}
+} catch (...) { return caught("pg_extract_open"); }
 
 extern "C" int64_t pg_extract_n_runs(const pg_extract* x) { return x ? (int64_t)x->run_labels.size() : -1; }
 extern "C" int64_t pg_extract_run_labels(const pg_extract* x, char* buf, int64_t cap, int64_t* offsets)
@@ -741,7 +741,7 @@ extern "C" int64_t pg_extract_run_labels(const pg_extract* x, char* buf, int64_t
 // cluster_of_run[n_runs]: cluster index (0 .. n_clusters - 1) or -1.  fq_start / bc_start: n_clusters + 1 byte offsets of every
 // cluster's slice in the two output blobs (pg_extract_copy)
 extern "C" int pg_extract_route(pg_ctx* ctx, pg_extract* x, const int32_t* cluster_of_run, int32_t n_clusters, int64_t* fq_start, int64_t* bc_start)
-{
+try {
     if (!ctx || !x || !cluster_of_run || n_clusters < 0 || n_clusters > 65000 || !fq_start || !bc_start) return fail(ctx, PG_ERR_INVALID, "pg_extract_route: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     for (int c = 0; c <= n_clusters; ++c) fq_start[c] = bc_start[c] = 0;
@@ -814,17 +814,17 @@ extern "C" int pg_extract_route(pg_ctx* ctx, pg_extract* x, const int32_t* clust
     CKR(cudaGetLastError());
     CKR(cudaStreamSynchronize(ctx->stream));
     return done(PG_OK);
-}
+} catch (...) { return caught("pg_extract_route"); }
 
 extern "C" int pg_extract_copy(pg_ctx* ctx, const pg_extract* x, char* fq_out, char* bc_out)
-{
+try {
     if (!ctx || !x) return fail(ctx, PG_ERR_INVALID, "pg_extract_copy: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     if (x->fq_total && fq_out) CK(cudaMemcpyAsync(fq_out, x->out_fq, (size_t)x->fq_total, cudaMemcpyDeviceToHost, ctx->stream));
     if (x->bc_total && bc_out) CK(cudaMemcpyAsync(bc_out, x->out_bc, (size_t)x->bc_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_extract_copy"); }
 
 
 // ---------------------------------------------------------------------------
@@ -833,7 +833,7 @@ extern "C" int pg_extract_copy(pg_ctx* ctx, const pg_extract* x, char* fq_out, c
 extern "C" int64_t pg_batch_n_words(const pg_batch* b) { return b ? b->n_words : -1; }
 
 extern "C" int pg_batch_window_keys(pg_ctx* ctx, pg_batch* b, int64_t w0, int64_t w1, int feature_windows, uint64_t* d_keys)
-{
+try {
     if (!ctx || !b || w0 < 0 || w1 < w0 || w1 > b->n_words || (w1 > w0 && !d_keys)) return fail(ctx, PG_ERR_INVALID, "pg_batch_window_keys: bad argument");
     if (w1 == w0) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -842,11 +842,11 @@ extern "C" int pg_batch_window_keys(pg_ctx* ctx, pg_batch* b, int64_t w0, int64_
     window_keys_kernel<<<(int)((w1 - w0 + 255) / 256), 256, 0, ctx->stream>>>(b->codes, mask, w0, w1, ctx->p.k, (unsigned long long*)d_keys);
     CK(cudaGetLastError());
     return PG_OK;
-}
+} catch (...) { return caught("pg_batch_window_keys"); }
 
 // d_sorted: the keys grouped by owner (owner 0 first); d_dest[i] = position of key i in d_sorted or -1; counts_out[world] on the host
 extern "C" int pg_keys_partition(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, int32_t world, uint64_t* d_sorted, int64_t* d_dest, int64_t* counts_out)
-{
+try {
     if (!ctx || n < 0 || world < 1 || world > 64 || !counts_out || (n && (!d_keys || !d_sorted || !d_dest))) return fail(ctx, PG_ERR_INVALID, "pg_keys_partition: bad argument");
     for (int r = 0; r < world; ++r) counts_out[r] = 0;
     if (!n) return PG_OK;
@@ -867,10 +867,10 @@ extern "C" int pg_keys_partition(pg_ctx* ctx, const uint64_t* d_keys, int64_t n,
     CK(cudaStreamSynchronize(ctx->stream));
     dfree(ctx, d_cnt);
     return PG_OK;
-}
+} catch (...) { return caught("pg_keys_partition"); }
 
 extern "C" int pg_table_add_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n)
-{
+try {
     if (!ctx || n < 0 || (n && !d_keys)) return fail(ctx, PG_ERR_INVALID, "pg_table_add_keys: bad argument");
     CK(cudaSetDevice(ctx->p.device));
     { int rc_ = table_ready(ctx); if (rc_) return rc_; }
@@ -886,10 +886,10 @@ extern "C" int pg_table_add_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n)
     }
     CK(cudaGetLastError());
     return check_overflow(ctx);
-}
+} catch (...) { return caught("pg_table_add_keys"); }
 
 extern "C" int pg_table_lookup_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t n, uint32_t* d_counts)
-{
+try {
     if (!ctx || n < 0 || (n && (!d_keys || !d_counts))) return fail(ctx, PG_ERR_INVALID, "pg_table_lookup_keys: bad argument");
     if (!n) return PG_OK;
     CK(cudaSetDevice(ctx->p.device));
@@ -899,12 +899,12 @@ extern "C" int pg_table_lookup_keys(pg_ctx* ctx, const uint64_t* d_keys, int64_t
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
-}
+} catch (...) { return caught("pg_table_lookup_keys"); }
 
 // abundance tallies of the windows that start in words [w0, w1) from counts that came back from their owners:
 // d_dest (32 per word, from pg_keys_partition) indexes d_counts_sorted (the counts in the order the keys were sent)
 extern "C" int pg_features_add_counts(pg_ctx* ctx, pg_features* f, pg_batch* b, int64_t w0, int64_t w1, const int64_t* d_dest, const uint32_t* d_counts_sorted)
-{
+try {
     if (!ctx || !f || !b || w0 < 0 || w1 < w0 || w1 > b->n_words) return fail(ctx, PG_ERR_INVALID, "pg_features_add_counts: bad argument");
     if (!f->row_of_group || !b->wg || !b->gstart) return fail(ctx, PG_ERR_STATE, "pg_features_add_counts: the feature set must come from pg_featurize2(PG_FEAT_NO_ABUNDANCE) of this batch");
     if (w1 == w0 || !f->rows) return PG_OK;
@@ -922,4 +922,4 @@ extern "C" int pg_features_add_counts(pg_ctx* ctx, pg_features* f, pg_batch* b, 
     abd_from_counts_kernel<<<grid_for((w1 - w0) * 32, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(P, w0, w1, (const long long*)d_dest, d_counts_sorted);
     CK(cudaGetLastError());
     return PG_OK;
-}
+} catch (...) { return caught("pg_features_add_counts"); }

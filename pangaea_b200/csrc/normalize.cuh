@@ -82,4 +82,52 @@ normalize_rows_kernel(const uint32_t* __restrict__ raw, int64_t rows, int dim, f
     }
 }
 
+// Rows of 4 n <= 512 elements (the production shapes: 400 and 136): one warp per row, the row read ONCE as 16-byte vectors
+// that stay in registers between the sum and the division, streamed past the caches in both directions (every byte is
+// touched once).  The kernel above remains for odd shapes.
+template <int VPL> // vectors per lane: ceil(dim / 4 / 32)
+__global__ void __launch_bounds__(256)
+normalize_rows_vec_kernel(const uint4* __restrict__ raw, int64_t rows, int nvec, float4* __restrict__ out, double* __restrict__ weights, int text_round)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) { // (r is warp-uniform)
+        const uint4* src = raw + r * nvec;
+        uint4 v[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) v[q] = lane + 32 * q < nvec ? __ldcs(src + lane + 32 * q) : make_uint4(0u, 0u, 0u, 0u);
+        auto val = [&](uint32_t x) { return text_round ? text_round6(x) : (unsigned long long)x; };
+        unsigned long long sum = 0, mx = 0;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+            const unsigned long long a = val(v[q].x), b = val(v[q].y), c = val(v[q].z), d = val(v[q].w);
+            sum += (a + b) + (c + d);
+            mx = max(max(mx, max(a, b)), max(c, d));
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        const double norm = sum ? (double)sum : 1.0;
+        const bool plain = (sum & (sum + 1ull)) == 0ull; // see normalize_rows_kernel
+        const double y = 1.0 / norm;
+        auto quot = [&](unsigned long long t) {
+            const double x = (double)t;
+            if (plain) return x / norm;
+            const double q = x * y;
+            return fma(fma(-norm, q, x), y, q);
+        };
+        float4* dst = out + r * nvec;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q)
+            if (lane + 32 * q < nvec)
+                __stcs(dst + lane + 32 * q, make_float4((float)quot(val(v[q].x)), (float)quot(val(v[q].y)), (float)quot(val(v[q].z)), (float)quot(val(v[q].w))));
+        if (weights && lane == 0) {
+            const double m = quot(mx);
+            weights[r] = m * m;
+        }
+    }
+}
+
 } // namespace pg

@@ -23,6 +23,7 @@
 namespace pg {
 
 constexpr int kTnfThreads = 256;
+constexpr int kTnfFoldMaxK = 4; // up to this tnf_k the flush folds a cloud's bins into its tnf_dim columns in shared memory (136 at k = 4)
 constexpr int kTnfSlots = 32; // clouds of a 256-word tile with private bins: 1 KB each at tnf_k = 4 (one cloud per read pair still fits)
 
 template <int TK>
@@ -35,9 +36,14 @@ tnf_kernel(const FeatParams P)
     const int n_slots = P.tnf_slots;                               // host: as many as fit (api.cu)
     uint32_t* bins = smem;                                         // [n_slots][nb] + 1 dummy
     uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + n_slots * nb + 1);
+    uint32_t* canon = reinterpret_cast<uint32_t*>(lut_s + nb);    // [warps][td] folded rows of the flush (tnf_k <= 4, api.cu)
+    uint32_t* direct = canon + (kTnfThreads / 32) * P.td;          // [2] a word of the tile went straight to the global matrix
+    const bool fold = tk <= kTnfFoldMaxK;
     for (int i = threadIdx.x; i < n_slots * nb + 1; i += blockDim.x) bins[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) lut_s[i] = P.lut[i];
+    if (fold && threadIdx.x < 2) direct[threadIdx.x] = 0u;
     __syncthreads();
+    uint32_t flushes = 0u; // parity of the flag in use
 
     const int64_t w_begin = (int64_t)blockIdx.x * P.words_per_cta;
     const int64_t w_end = min(P.n_words, w_begin + P.words_per_cta);
@@ -80,7 +86,7 @@ tnf_kernel(const FeatParams P)
                             const uint32_t u = i == 0 ? s0 : (i < 16 ? __funnelshift_r(s0, s1, 2 * i) : (i == 16 ? s1 : __funnelshift_r(s1, s2, 2 * i - 32)));
                             atomicAdd(my + ((tvalid & (1u << i)) ? (u & tmask) : dmy), 1u);
                         }
-                    } else { // more clouds in this tile than slots
+                    } else { // more clouds in this tile than slots (they own no slot: no conflict with the stores of the flush)
                         uint32_t* tnf_row = P.tnf + (int64_t)row * P.td;
                         for (int i = 0; i < 32; ++i)
                             if (tvalid & (1u << i)) {
@@ -112,6 +118,7 @@ tnf_kernel(const FeatParams P)
                     }
                 } else {
                 // three clouds in one word (clouds shorter than 32 bases) or no bins left: resolve the cloud per position
+                if (fold) direct[flushes & 1u] = 1u; // these REDs may hit rows the flush would otherwise store
                 int64_t gg = g;
                 int64_t next_start = __ldg(P.gstart + gg + 1);
                 int32_t row = __ldg(P.row_of_group + gg);
@@ -133,15 +140,49 @@ tnf_kernel(const FeatParams P)
         const bool carry = g_hi == g_lo && tile_end < w_end && (__ldg(P.wg + tile_end) & ~kWordMixed) == g_lo;
         if (!carry) {
             __syncthreads();
-            const uint32_t ns = min((uint32_t)n_slots, g_hi - g_lo + 1u);
-            for (uint32_t s = 0; s < ns; ++s) {
-                const int32_t row = __ldg(P.row_of_group + g_lo + s);
-                if (row < 0) continue;
-                uint32_t* src = bins + s * nb;
-                uint32_t* dst = P.tnf + (int64_t)row * P.td;
-                for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-                    const uint32_t v = src[b];
-                    if (v) { atomicAdd(dst + lut_s[b], v); src[b] = 0u; }
+            const uint32_t n_here = g_hi - g_lo + 1u;
+            const uint32_t ns = min((uint32_t)n_slots, n_here);
+            if (fold) {
+                // one warp per cloud slot (the loads of the row numbers of different slots are in flight together - a block-wide
+                // loop over the slots serialises them: 27 dependent round trips per tile with one cloud per read pair).  The
+                // 4^k raw bins are folded into the tnf_dim columns in shared memory; a cloud that lies strictly inside the
+                // tile (not its first, not its last) is complete here and nobody else touches its row: plain coalesced
+                // stores, zeros included.  The two clouds at the edges continue in other tiles: reductions.
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                uint32_t* cw = canon + warp * P.td;
+                const bool any_direct = direct[flushes & 1u] != 0u;
+                if (threadIdx.x == 0) direct[(flushes + 1u) & 1u] = 0u; // (written by the words of the next tile, after the barrier below)
+                for (uint32_t s = warp; s < ns; s += kTnfThreads / 32) {
+                    const int32_t row = __ldg(P.row_of_group + g_lo + s);
+                    if (row < 0) continue; // (dropped clouds were never tallied)
+                    uint32_t* src = bins + s * nb;
+                    for (int c = lane; c < P.td; c += 32) cw[c] = 0u;
+                    __syncwarp();
+                    for (int b = lane; b < nb; b += 32) {
+                        const uint32_t v = src[b];
+                        if (v) { atomicAdd(cw + lut_s[b], v); src[b] = 0u; }
+                    }
+                    __syncwarp();
+                    const bool whole = s > 0u && s + 1u < n_here && !any_direct;
+                    uint32_t* dst = P.tnf + (int64_t)row * P.td;
+                    for (int c = lane; c < P.td; c += 32) {
+                        const uint32_t v = cw[c];
+                        if (whole) dst[c] = v;
+                        else if (v) atomicAdd(dst + c, v);
+                    }
+                    __syncwarp();
+                }
+                ++flushes;
+            } else {
+                for (uint32_t s = 0; s < ns; ++s) {
+                    const int32_t row = __ldg(P.row_of_group + g_lo + s);
+                    if (row < 0) continue;
+                    uint32_t* src = bins + s * nb;
+                    uint32_t* dst = P.tnf + (int64_t)row * P.td;
+                    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                        const uint32_t v = src[b];
+                        if (v) { atomicAdd(dst + lut_s[b], v); src[b] = 0u; }
+                    }
                 }
             }
             __syncthreads();
