@@ -1313,11 +1313,18 @@ try {
                 const size_t avg_cloud = (size_t)std::max<int64_t>(1, b->n_bytes / std::max<int64_t>(1, n_groups));
                 const size_t want_slots = std::min<size_t>(kTnfSlots, std::max<size_t>(4, (size_t)kTnfThreads * 32 / avg_cloud + 3));
                 P.tnf_slots = (int)std::max<size_t>(2, std::min<size_t>(want_slots, (32 * 1024) / (nb * sizeof(uint32_t))));
+                // Tiny clouds (one per read pair: ~27 per tile): flush with one warp per cloud, folded columns, stores for the
+                // clouds that lie inside the tile - and the kernel ALONE on the GPU: next to the look-ups it takes 5x as long
+                // and doubles them (100 M pairs 2x150: TNF 60 ms + look-ups 116 ms in sequence, 301 + 244 ms side by side;
+                // profiles/bench_r02_c4_tnf_ab.txt).  Clouds of many tiles: block-wide flush of the one or two slots in use,
+                // beside the sweep (12.6 ms hidden at the headline workload).
+                const bool tiny = avg_cloud < 2048;
+                { const char* e = getenv("PG_TNF_FOLD"); P.tnf_fold = e ? atoi(e) : (tiny ? 1 : 0); } // (A/B switch)
                 const size_t smem_t = ((size_t)P.tnf_slots * nb + 2) * sizeof(uint32_t) + 2 * nb
                                       + (P.tnf_k <= kTnfFoldMaxK ? ((size_t)(kTnfThreads / 32) * P.td + 2) * sizeof(uint32_t) : 0);
                 // The TNF kernel is bound by shared-memory atomics, the look-up sweep below by L1 gathers: with a few CTAs per SM
                 // on the second stream it runs NEXT TO the sweep instead of before it.
-                const bool side = ctx->tnf_overlap > 0;
+                const bool side = ctx->tnf_overlap > 0 && (!tiny || getenv("PG_TNF_OVERLAP"));
                 const int64_t max_cta = (int64_t)ctx->sm_count * (side ? ctx->tnf_overlap : 8);
                 const int64_t n_cta = std::min<int64_t>(max_cta, (b->n_words + kTnfThreads - 1) / kTnfThreads);
                 int64_t wpc = (b->n_words + n_cta - 1) / n_cta;

@@ -35,6 +35,7 @@
 // (count_kmer.cpp:90-93), maps cloud -> row and reduces equal (row, bin) pairs inside the warp before one RED into the
 // abundance matrix.
 #pragma once
+#include <type_traits>
 #include "featurize.cuh"
 #include "scan.cuh"
 #include "table.cuh"
@@ -383,11 +384,9 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
         }
         // every lane issues the atomic: windows that emit nothing go to the dummy row, so the loop has
         // no divergence bookkeeping (a conditional shared atomic compiles to BSSY/BRA/ATOMS/BSYNC)
-#pragma unroll 1
-        for (int trip = 0; trip < (MODE == kScatterCount ? 1 : MODE == kScatterFeat ? 2 : 3); ++trip) {
-            const uint32_t v = trip == 0 ? v0 : trip == 1 ? v1 : v2;
-            const uint32_t d = trip == 0 ? d0 : trip == 1 ? d1 : delta_bits(kDeltaCountOnly);
-            if (v == 0u) continue; // trips 1 and 2 are rare: one word per cloud / lower-case bases
+        // one pass over the 32 windows of the word: valid windows `v`, delta bits `d` (`dB` for the windows in `selB` when MERGED)
+        auto pass = [&](auto merged, const uint32_t v, const uint32_t d, const uint32_t dB, const uint32_t selB) {
+            constexpr bool MERGED = decltype(merged)::value;
             // four windows at a time: the four returning atomics are issued back to back, so their latency overlaps
             uint32_t yb[4];
             auto hand_out = [&](int i, uint32_t y) {
@@ -402,7 +401,8 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
                 for (int q = 0; q < 4; ++q) // a row that overflows is redone below
                 {
                     PG_CHECK(bk[q] <= (uint32_t)kMaxBuckets && (bk[q] == (uint32_t)kMaxBuckets || (int)bk[q] < Q.geo.n_buckets));
-                    stage[bk[q] * STRIDE + min(slot[q], (uint32_t)(CAP - 1))] = FEAT ? ((yb[q] & kEntryIndexBits) | d) : yb[q];
+                    const uint32_t dq = MERGED ? ((selB & (1u << (i - 3 + q))) ? dB : d) : d;
+                    stage[bk[q] * STRIDE + min(slot[q], (uint32_t)(CAP - 1))] = FEAT ? ((yb[q] & kEntryIndexBits) | dq) : yb[q];
                 }
             };
             // ptxas would hoist the 32 loop-invariant window extractions out of the trip loop and spill them: a shuffle
@@ -410,6 +410,18 @@ bucket_scatter_kernel(const ScatterParams Q, const FeatParams P)
             lo = __shfl_sync(__activemask(), lo, lane);
             hi = __shfl_sync(__activemask(), hi, lane);
             for_each_window<KT>(lo, hi, k, hand_out);
+        };
+        // Words with a cloud boundary are one per cloud: rare with 20 KB clouds (their second cloud gets its own trip, which
+        // almost no warp takes), but every tenth word with one cloud per read pair - then nearly every warp holds one and
+        // the second trip would double the work of the whole kernel: such warps pick the delta per window in ONE pass.
+        const bool merge = FEAT && __any_sync(0xffffffffu, v1 != 0u);
+        if (FEAT && merge && (v0 | v1) != 0u) pass(std::true_type{}, v0 | v1, d0, d1, v1);
+#pragma unroll 1
+        for (int trip = (FEAT && merge) ? 2 : 0; trip < (MODE == kScatterCount ? 1 : MODE == kScatterFeat ? 2 : 3); ++trip) {
+            const uint32_t v = trip == 0 ? v0 : trip == 1 ? v1 : v2;
+            const uint32_t d = trip == 0 ? d0 : trip == 1 ? d1 : delta_bits(kDeltaCountOnly);
+            if (v == 0u) continue; // trips 1 and 2 are rare: one word per cloud / lower-case bases
+            pass(std::false_type{}, v, d, 0u, 0u);
         }
         bulk_store_fence(); // the rows were written through the generic proxy; the copy engine reads them through the async proxy
         __syncthreads();

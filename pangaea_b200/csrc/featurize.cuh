@@ -45,6 +45,7 @@ struct FeatParams {
     const int32_t* row_lb;      // n_groups: rows emitted before cloud g
     int32_t tnf_k, vs, td;
     int32_t tnf_slots;          // tnf.cuh: cloud slots with block-private bins
+    int32_t tnf_fold;           // tnf.cuh: flush with one warp per slot, folded columns, stores for whole clouds
     uint32_t ws, clamp;         // clamp = min(ws * vs, 2^32-1): counts >= clamp fall outside the histogram
     uint32_t magic;             // ceil(2^32 / ws) when use_magic
     int32_t use_magic;

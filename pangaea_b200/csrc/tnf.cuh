@@ -38,7 +38,7 @@ tnf_kernel(const FeatParams P)
     uint16_t* lut_s = reinterpret_cast<uint16_t*>(bins + n_slots * nb + 1);
     uint32_t* canon = reinterpret_cast<uint32_t*>(lut_s + nb);    // [warps][td] folded rows of the flush (tnf_k <= 4, api.cu)
     uint32_t* direct = canon + (kTnfThreads / 32) * P.td;          // [2] a word of the tile went straight to the global matrix
-    const bool fold = tk <= kTnfFoldMaxK;
+    const bool fold = tk <= kTnfFoldMaxK && P.tnf_fold != 0;
     for (int i = threadIdx.x; i < n_slots * nb + 1; i += blockDim.x) bins[i] = 0u;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) lut_s[i] = P.lut[i];
     if (fold && threadIdx.x < 2) direct[threadIdx.x] = 0u;
