@@ -106,6 +106,7 @@ SIGNATURES = {
     "pg_fastq_group_label": (C.c_char_p, [_vp, _i64]),
     "pg_fastq_group_labels": (_i64, [_vp, _vp, _i64, _vp]),
     "pg_mem_info": (_int, [_vp, _P(_i64), _P(_i64)]),
+    "pg_trim": (_int, [_vp]),
     "pg_ingest_text": (_int, [_vp, _vp, _i64, _int, C.c_char_p, _i64, _P(_i32), _P(_i64), _P(_vp), _P(_vp)]),
     "pg_ingest_n_groups": (_i64, [_vp]),
     "pg_ingest_group_keep": (_vp, [_vp]),
@@ -394,6 +395,10 @@ class Context:
         f, t = _i64(), _i64()
         self._ck(lib().pg_mem_info(self.h, C.byref(f), C.byref(t)))
         return int(f.value), int(t.value)
+
+    def trim(self):
+        """release the idle device memory the ctx keeps for reuse (live batches / features / the table stay)"""
+        self._ck(lib().pg_trim(self.h))
 
     # ---- batches -------------------------------------------------------------
     def upload(self, reads: pg_reads, keepalive=None) -> Batch:

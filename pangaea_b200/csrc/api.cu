@@ -50,6 +50,8 @@ struct Workspace {
 struct BigCache {
     std::unordered_map<void*, size_t> live;   // block -> capacity
     std::multimap<size_t, void*> free_blocks; // capacity -> block
+    std::unordered_map<void*, uint64_t> freed_at; // idle block -> value of `clock` when it was returned
+    uint64_t clock = 0;
     size_t free_bytes = 0;
 };
 
@@ -216,16 +218,23 @@ static cudaError_t ws_get(pg_ctx* ctx, Workspace& w, size_t bytes)
 }
 
 constexpr size_t kBigBlock = 1u << 20;          // smaller requests stay with cudaMallocAsync
-constexpr size_t kBigCacheLimit = 48ull << 30;  // idle bytes kept before the largest blocks are released
+constexpr size_t kBigCacheLimit = 48ull << 30;  // idle bytes kept; beyond it the blocks idle longest are released, down to 3/4 of it
+static const bool g_big_lru = !(getenv("PG_BIG_CACHE") && !strcmp(getenv("PG_BIG_CACHE"), "largest")); // (A/B switch: round-1 policy)
 
 static void big_trim(pg_ctx* ctx, size_t keep_bytes)
 {
     if (ctx->big.free_bytes <= keep_bytes) return;
     cudaStreamSynchronize(ctx->stream); // a cached block may still be read by queued work
+    // the block that has been idle longest goes first: what a streamed job allocates per batch (feature matrices, 43 GB at
+    // 10 M rows) comes back every batch and stays, what it will not ask for again (the packed streams of finished batches)
+    // ages out.  (Largest-first released exactly the matrices: a 16 GB cudaMalloc + cudaFree per batch.)
     while (ctx->big.free_bytes > keep_bytes && !ctx->big.free_blocks.empty()) {
-        auto it = std::prev(ctx->big.free_blocks.end());
+        auto it = g_big_lru ? ctx->big.free_blocks.begin() : std::prev(ctx->big.free_blocks.end());
+        for (auto j = ctx->big.free_blocks.begin(); g_big_lru && j != ctx->big.free_blocks.end(); ++j)
+            if (ctx->big.freed_at[j->second] < ctx->big.freed_at[it->second]) it = j;
         cudaFree(it->second);
         ctx->big.free_bytes -= it->first;
+        ctx->big.freed_at.erase(it->second);
         ctx->big.free_blocks.erase(it);
     }
 }
@@ -238,13 +247,15 @@ static cudaError_t big_alloc(pg_ctx* ctx, void** p, size_t bytes)
         *p = it->second;
         ctx->big.live[*p] = it->first;
         ctx->big.free_bytes -= it->first;
+        ctx->big.freed_at.erase(it->second);
         ctx->big.free_blocks.erase(it);
         return cudaSuccess;
     }
     cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess) { // out of memory: give the idle blocks back and try once more
+    while (e != cudaSuccess && !ctx->big.free_blocks.empty()) { // out of memory: give idle blocks back, oldest first, until it fits
         cudaGetLastError();
-        big_trim(ctx, 0);
+        const size_t idle = ctx->big.free_bytes;
+        big_trim(ctx, g_big_lru ? (idle > bytes ? idle - bytes : 0) : 0);
         e = cudaMalloc(p, bytes);
     }
     if (e == cudaSuccess) ctx->big.live[*p] = bytes;
@@ -265,9 +276,12 @@ static void dfree(pg_ctx* ctx, void* p)
     auto it = ctx->big.live.find(p);
     if (it == ctx->big.live.end()) { cudaFreeAsync(p, ctx->stream); return; }
     ctx->big.free_blocks.insert({ it->second, p });
+    ctx->big.freed_at[p] = ++ctx->big.clock;
     ctx->big.free_bytes += it->second;
     ctx->big.live.erase(it);
-    big_trim(ctx, kBigCacheLimit);
+    // (hysteresis: a trim synchronises the stream and cudaFree drains the device - once every few batches of a streamed job, not at
+    // every free of a job that sits at the limit)
+    if (ctx->big.free_bytes > kBigCacheLimit) big_trim(ctx, g_big_lru ? kBigCacheLimit / 4 * 3 : kBigCacheLimit);
 }
 
 // ---------------------------------------------------------------------------
@@ -426,7 +440,8 @@ try {
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<15, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_scatter_kernel<0, kScatterShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<true>)));
     CKC(cudaFuncSetAttribute(bucket_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
-    CKC(cudaFuncSetAttribute(bucket_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_collect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(bucket_collect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(sub_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubWords * 4 + 16));
     CKC(cudaFuncSetAttribute(tnf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CKC(cudaFuncSetAttribute(tnf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -480,6 +495,18 @@ try {
     *total_bytes = (int64_t)t;
     return PG_OK;
 } catch (...) { return caught("pg_mem_info"); }
+
+extern "C" int pg_trim(pg_ctx* ctx)
+try {
+    if (!ctx) return fail(nullptr, PG_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(ctx->p.device));
+    big_trim(ctx, 0); // (synchronises the stream first)
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& w : ctx->stash_pool) cudaFree(w.p);
+    ctx->stash_pool.clear();
+    if (ctx->mempool) CK(cudaMemPoolTrimTo(ctx->mempool, 0));
+    return PG_OK;
+} catch (...) { return caught("pg_trim"); }
 
 // ---------------------------------------------------------------------------
 // timing
@@ -1380,7 +1407,8 @@ try {
             while (c_slots > 2 && ((size_t)c_slots * P.vs + c_slots) * 4 > 190 * 1024) --c_slots;
             const size_t c_smem = ((size_t)c_slots * P.vs + c_slots) * 4;
             int c_occ = 1;
-            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, bucket_collect_kernel, kCollectThreads, c_smem));
+            const bool c_hot = avg_cloud >= 2048; // (PG_FEAT_APPLY=0 on large clouds; the automatic choice uses collect for tiny clouds only)
+            CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, bucket_collect_kernel<false>, kCollectThreads, c_smem));
             auto lookup_collect = [&](uint32_t* entries, const int32_t* meta, const uint2* runs, const BucketGeom& geo, const unsigned long long* fill,
                                       int64_t w0, int64_t w1, bool shared_entries, bool sweep) {
                 ctx->launches[T_GROUP] += 1; // the ticket reset, booked with the other housekeeping kernels
@@ -1402,7 +1430,8 @@ try {
                 const int64_t n_tiles = (w1 - w0 + C.tile_words - 1) / C.tile_words;
                 const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * std::max(c_occ, 1)));
                 Timed t(ctx, T_COLLECT, 1);
-                bucket_collect_kernel<<<grid, kCollectThreads, c_smem, ctx->stream>>>(C, P);
+                if (c_hot) bucket_collect_kernel<true><<<grid, kCollectThreads, c_smem, ctx->stream>>>(C, P);
+                else bucket_collect_kernel<false><<<grid, kCollectThreads, c_smem, ctx->stream>>>(C, P);
             };
             if (reuse) {
                 for (auto& sgm : b->stash) lookup_collect(sgm.entries, sgm.meta, sgm.runs, sgm.geo, sgm.fill, sgm.w0, sgm.w1, true, b->stash_sweep);

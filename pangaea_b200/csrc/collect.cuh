@@ -83,6 +83,10 @@ struct CollectParams {
     int shared;                  // 1: deltas are CLOUD deltas against the tile's first cloud; 0: ROW deltas against row_lb of that cloud
 };
 
+// HOT: the three most frequent (cloud, bin) keys of a run are tallied in registers - pays for clouds of many reads (a run of
+// 230 entries holds a few clouds whose k-mers share a few bins); with one cloud per read pair a run spans ~50 clouds and no
+// key repeats: the vote and the three compares per entry are dead weight (ncu: 79 thread instructions per window).
+template <bool HOT>
 __global__ void __launch_bounds__(kCollectThreads)
 bucket_collect_kernel(const CollectParams C, const FeatParams P)
 {
@@ -115,9 +119,10 @@ bucket_collect_kernel(const CollectParams C, const FeatParams P)
             if (!r.n) continue;
             const uint32_t* src = C.entries + (unsigned long long)b * C.geo.cap + r.off;
             // the three most frequent keys among the run's first 32 entries are tallied in registers
+            uint32_t hot[3] = { 0u, 0u, 0u };
+            if (HOT) {
             uint32_t s = lane < r.n ? __ldg(src + lane) : 0u;
             uint32_t key_s = ((s >> 3) & kBinField) ? ((delta_of_entry(s) << 14) | ((s >> 3) & kBinField)) : 0u;
-            uint32_t hot[3];
 #pragma unroll
             for (int h = 0; h < 3; ++h) {
                 const uint32_t peers = __match_any_sync(0xffffffffu, key_s);
@@ -126,6 +131,7 @@ bucket_collect_kernel(const CollectParams C, const FeatParams P)
                 const int who = 31 - (int)(best & 31u);
                 hot[h] = best >> 5 ? __shfl_sync(0xffffffffu, key_s, who) : 0u;
                 if (key_s == hot[h]) key_s = 0u; // out of the next vote
+            }
             }
             uint32_t c0 = 0u, c1 = 0u, c2 = 0u;
             for (uint32_t i0 = 8u * lane; i0 < r.n; i0 += 256u) { // a lane takes eight consecutive entries (runs start 16 B aligned and are padded to 32)
@@ -138,9 +144,9 @@ bucket_collect_kernel(const CollectParams C, const FeatParams P)
                     if (i0 + u >= r.n || !f) continue;   // (padding carries bin field 0 after the lookup)
                     const uint32_t delta = delta_of_entry(v[u]);
                     const uint32_t key = (delta << 14) | f;
-                    if (key == hot[0]) ++c0;
-                    else if (key == hot[1]) ++c1;
-                    else if (key == hot[2]) ++c2;
+                    if (HOT && key == hot[0]) ++c0;
+                    else if (HOT && key == hot[1]) ++c1;
+                    else if (HOT && key == hot[2]) ++c2;
                     else if (delta < (uint32_t)C.slots) atomicAdd(&hist[delta * P.vs + (f - 1u)], 1u);
                     else { // more clouds in the tile than slots: straight to the matrix
                         int32_t row = (int32_t)delta + base;
@@ -149,6 +155,7 @@ bucket_collect_kernel(const CollectParams C, const FeatParams P)
                     }
                 }
             }
+            if constexpr (HOT) {
 #pragma unroll
             for (int d = 16; d; d >>= 1) {
                 c0 += __shfl_xor_sync(0xffffffffu, c0, d);
@@ -167,16 +174,21 @@ bucket_collect_kernel(const CollectParams C, const FeatParams P)
                     }
                 }
             }
+            }
         }
         __syncthreads();
-        // rows leave shared memory: non-zero bins are reduced into the (zeroed) matrix - a cloud that spans tiles or CTAs adds up there
-        for (int i = threadIdx.x; i < n_hist; i += kCollectThreads) {
-            const uint32_t v = hist[i];
-            if (!v) continue;
-            hist[i] = 0u;
-            const int sl = i / P.vs;
+        // rows leave shared memory: non-zero bins are reduced into the (zeroed) matrix - a cloud that spans tiles or CTAs adds up
+        // there.  One warp per slot: the row number is read once and no index is divided by the row length.
+        for (int sl = warp; sl < C.slots; sl += kCollectThreads / 32) {
             const int32_t row = slot_row[sl];
-            if (row >= 0) atomicAdd(P.abd + (int64_t)row * P.vs + (i - sl * P.vs), v);
+            uint32_t* h = hist + sl * P.vs;
+            uint32_t* dst = P.abd + (int64_t)max(row, 0) * P.vs;
+            for (int i = lane; i < P.vs; i += 32) {
+                const uint32_t v = h[i];
+                if (!v) continue;
+                h[i] = 0u;
+                if (row >= 0) atomicAdd(dst + i, v);
+            }
         }
         __syncthreads();
     }

@@ -109,6 +109,7 @@ class Feature:
                 abundance, tnf = _reference_text_rounding(abundance), _reference_text_rounding(tnf)
             self.timing = {n: ctx.timing(w)[0] for n, w in (("pack", 0), ("count", 1), ("group", 2), ("featurize", 3), ("normalize", 4))}
             self.features, self._ctx = feats, ctx
+            ctx.trim()  # the VAE comes next on this GPU: hand the idle scratch (partitions, packed streams) back to the driver
             if write_cache:  # same pickles the reference leaves: DataFrame, column 0 = label
                 for path, m in ((self._abd_pkl(), abundance), (self._tnf_pkl(), tnf)):
                     df = pd.DataFrame(m)

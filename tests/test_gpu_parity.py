@@ -603,6 +603,37 @@ def test_two_batches_one_table(tmp_path, oracle):
     torch.cuda.synchronize()
 
 
+def test_trim_releases_idle_memory_and_the_ctx_keeps_working(tmp_path, oracle):
+    """pg_trim: the blocks the ctx caches for reuse (freed matrices, partitions, packed streams) go back to the driver; live
+    objects - a batch, its feature set, the k-mer table - are untouched and the next call allocates afresh."""
+    data = synth.generate(n_barcodes=200, mean_pairs=20, read_len=100, n_genomes=3, genome_len=60_000, frag_len=8_000, seed=77)
+    path = synth.write_interleaved(str(tmp_path / "t.fq"), data)
+    names, abd, tnf = oracle.featurize(path, None)
+    ctx = _ctx()
+    fq = _lib.Fastq(path)
+    held = ctx.upload(fq.reads)
+    ctx.count(held)
+    first = ctx.featurize(held, fq.group_keep, fq.n_groups)
+    for _ in range(3):  # churn: every round returns its blocks to the cache
+        b = ctx.upload(fq.reads)
+        f = ctx.featurize(b, fq.group_keep, fq.n_groups)
+        f.normalize()
+        f.free(); b.free()
+    free_before, total = ctx.mem_info()
+    ctx.trim()
+    free_after, _ = ctx.mem_info()
+    assert 0 < free_after <= total and free_after >= free_before - (64 << 20)  # (what was idle is now plain free memory)
+    g_abd, g_tnf = first.raw()  # made before the trim
+    assert np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
+    again = ctx.featurize(held, fq.group_keep, fq.n_groups)  # after it
+    a_abd, a_tnf = again.raw()
+    assert _names(fq, again) == list(names)
+    assert np.array_equal(a_abd, abd) and np.array_equal(a_tnf, tnf)
+    ctx.trim()  # idempotent, also with nothing cached
+    first.free(); again.free(); held.free()
+    ctx.close()
+
+
 def test_pipelined_upload_with_unpaired_reads_and_lower_case(tmp_path, oracle):
     """pg_extract_features on > 1 MB goes through the chunked upload (the count pass runs while later chunks are still
     crossing PCIe).  Paired files with mismatching R1/R2 names (counted, but in no cloud: PG_READ_NOFEAT) and lower-case
