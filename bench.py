@@ -54,7 +54,7 @@ CONFIGS = {
                pairs_per_barcode=100, n_genomes=400, seed=3, min_length=2000, scaling="strong", barcode_len=18, batch_pairs=25_000_000),
     "c4": dict(workload="hybrid-mode plain short reads 2x150bp (no barcodes), 300M read pairs, per-read abundance features",
                pairs=300_000_000, read_len=150, pairs_per_barcode=1, n_genomes=400, seed=4, min_length=0, scaling="strong", barcode_len=18,
-               batch_pairs=10_000_000),
+               batch_pairs=7_000_000),  # two full segments per batch; 30 GB of matrices per batch leave room in HBM next to the 43 packed batches
     "c5": dict(workload="synthetic stLFR 2x100bp, 1B read pairs, 5M barcodes, k-mer table sharded over 8 B200", pairs=1_000_000_000,
                read_len=100, pairs_per_barcode=200, n_genomes=1000, seed=5, min_length=2000, scaling="strong", barcode_len=16,
                batch_pairs=62_500_000),

@@ -97,9 +97,9 @@ int pg_tnf_dim(int tnf_k);
 int pg_synchronize(pg_ctx* ctx);
 /* free / total device memory as the driver reports it, plus what this ctx holds idle in its caches (reusable by it) */
 int pg_mem_info(pg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
-/* give the idle device memory this ctx caches for reuse (freed matrices, partitions, packed streams: up to 48 GB, the block
- * idle longest released first) back to the driver - e.g. before the VAE of src/pangaea.py:91 starts on the same GPU.  Live
- * batches, feature sets and the k-mer table are untouched. */
+/* give the idle device memory this ctx caches for reuse (freed matrices, partitions, packed streams: up to 48 GB) back to
+ * the driver - e.g. before the VAE of src/pangaea.py:91 starts on the same GPU.  Live batches, feature sets and the k-mer
+ * table are untouched. */
 int pg_trim(pg_ctx* ctx);
 /* the cudaStream_t every launch of this ctx goes to (for CUDA-event timing by the caller) */
 void* pg_stream(pg_ctx* ctx);
