@@ -132,7 +132,7 @@ class ClockSampler:
             return
         try:
             self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -189,8 +189,8 @@ def design_bytes(n_bytes, entries_count, windows_feat, rows, sliced, vs=400, td=
 
 KERNEL_OF_STAGE = {"pack": "pack_kernel", "count_scatter": "bucket_scatter_kernel<15,shared>", "count_split": "bucket_split_kernel",
                    "count_apply": "sub_apply_kernel", "group": "flag_count/tile_scan/group_starts/row_assign/word_groups kernels", "tnf": "tnf_kernel<4>",
-                   "feat_scatter": "bucket_scatter_kernel<15,feat>", "feat_apply": "bucket_lookup_kernel", "feat_collect": "bucket_collect_kernel",
-                   "normalize": "normalize_rows_kernel"}
+                   "feat_scatter": "bucket_scatter_kernel<15,feat>", "feat_apply": "bucket_apply_feat_kernel", "feat_collect": "bucket_collect_kernel",
+                   "normalize": "normalize_rows_vec_kernel"}
 STAGE_SLOTS = (("pack", 0), ("count_scatter", 6), ("count_split", 9), ("count_apply", 1), ("group", 2), ("tnf", 8), ("feat_scatter", 7), ("feat_apply", 3),
                ("feat_collect", 10), ("normalize", 4))
 # which §8d pass a kernel belongs to
@@ -220,7 +220,10 @@ def build_roofline(stage_ms, stage_launches, pairs_per_step, read_len, rows, n_b
     pass_bytes["featurize"] += pass_bytes.pop("rows_raw")  # the int32 tallies are written by the featurize pass
     timed = {k: v for k, v in stage_ms.items() if k in PASS_OF_STAGE and v > 0}
     dom = max(timed, key=lambda n: timed[n])
-    kname = KERNEL_OF_STAGE[dom] if sliced else {"count_apply": "count_kernel", "feat_apply": "featurize_kernel"}.get(dom, KERNEL_OF_STAGE[dom])
+    kernel_of = dict(KERNEL_OF_STAGE)
+    if stage_ms.get("feat_collect", 0) > 0:  # tiny clouds: the featurize pass is look-up + collect instead of the single sweep
+        kernel_of["feat_apply"] = "bucket_lookup_kernel"
+    kname = kernel_of[dom] if sliced else {"count_apply": "count_kernel", "feat_apply": "featurize_kernel"}.get(dom, kernel_of[dom])
     dom_pass = PASS_OF_STAGE[dom]
     # the dominant kernel is charged with its whole pass's §8d bytes (the other kernels of the pass are listed beside it)
     per_seg = {"count_scatter": 3 if shared else 2, "feat_scatter": 2, "count_split": 2, "count_apply": 3}.get(dom, 1)
@@ -242,12 +245,12 @@ def build_roofline(stage_ms, stage_launches, pairs_per_step, read_len, rows, n_b
     for st, (what, ops) in floors.items():
         if stage_ms.get(st, 0) > 0:
             floor_ms = ops / ATTAINABLE[what] * 1e3
-            attainable[KERNEL_OF_STAGE[st]] = {"bound": what, "ops_per_s": ATTAINABLE[what], "floor_ms": round(floor_ms, 2),
+            attainable[kernel_of[st]] = {"bound": what, "ops_per_s": ATTAINABLE[what], "floor_ms": round(floor_ms, 2),
                                                 "ms": round(stage_ms[st], 2), "frac_of_attainable": round(floor_ms / stage_ms[st], 3)}
     for st in ("pack", "normalize"):
         if stage_ms.get(st, 0) > 0:
             floor_ms = design[st] / (peak * 1e9) * 1e3
-            attainable[KERNEL_OF_STAGE[st]] = {"bound": "hbm_stream", "floor_ms": round(floor_ms, 2), "ms": round(stage_ms[st], 2),
+            attainable[kernel_of[st]] = {"bound": "hbm_stream", "floor_ms": round(floor_ms, 2), "ms": round(stage_ms[st], 2),
                                                 "frac_of_attainable": round(floor_ms / stage_ms[st], 3)}
     return {"bound": "hbm", "kernel": kname, "pass": dom_pass, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": load_traffic().get(kname), "peak_source": peak_src,
