@@ -1173,7 +1173,12 @@ __global__ void min_group_len_kernel(const int64_t* __restrict__ gstart, int64_t
     if (g < n_groups && gstart[g + 1] > gstart[g]) len = (unsigned long long)(gstart[g + 1] - gstart[g]);
 #pragma unroll
     for (int d = 16; d; d >>= 1) len = min(len, __shfl_xor_sync(0xffffffffu, len, d));
-    if ((threadIdx.x & 31) == 0 && len != ~0ull) atomicMin(out, len);
+    __shared__ unsigned long long block_min; // one global atomic per CTA: with millions of clouds they all hit one address
+    if (threadIdx.x == 0) block_min = ~0ull;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && len != ~0ull) atomicMin(&block_min, len);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_min != ~0ull) atomicMin(out, block_min);
 }
 
 // Cloud structure that follows from the read flags alone: NOFEAT reads masked out of the feature mask,
@@ -1222,8 +1227,13 @@ static int group_stage_a(pg_ctx* ctx, pg_batch* b, bool want_wg, bool packed)
     }
     if (want_wg && !b->wg && b->n_words) { // word -> cloud map of the streaming kernels
         CK(dmalloc(ctx, &b->wg, (size_t)b->n_words));
-        word_groups_kernel<false><<<grid_for(b->n_groups * 32, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg);
-        word_groups_kernel<true><<<(int)std::min<int64_t>(b->n_groups, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg);
+        const size_t max_big = (size_t)(b->n_words / kBigCloudWords) + 2; // clouds of more than kBigCloudWords words: they are disjoint
+        uint32_t* big_list = nullptr; // [0] = how many, then the clouds
+        CK(dmalloc(ctx, &big_list, max_big + 1));
+        CK(cudaMemsetAsync(big_list, 0, sizeof(uint32_t), ctx->stream));
+        word_groups_kernel<false><<<grid_for(b->n_groups * 32, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg, big_list + 1, big_list);
+        word_groups_kernel<true><<<(int)std::min<int64_t>((int64_t)max_big, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(b->gstart, b->n_groups, b->n_bytes, b->wg, big_list + 1, big_list);
+        dfree(ctx, big_list);
         CK(cudaGetLastError());
     }
     return PG_OK;

@@ -175,19 +175,28 @@ row_assign_kernel(const uint8_t* __restrict__ emit, int64_t n_groups, const int3
 constexpr uint32_t kWordMixed = 0x80000000u;
 constexpr int64_t kBigCloudWords = 8192;
 
+// !BIG: one warp per cloud; clouds of more than kBigCloudWords words are only noted in big_list (at most n_words /
+// kBigCloudWords + 1 of them fit a stream).  BIG: one CTA per listed cloud.  (The BIG pass used to walk ALL clouds looking for
+// big ones: 5 900 dependent loads per CTA with one cloud per read pair - 3 ms of the 6.7 ms grouping of a 7 M-cloud batch.)
 template <bool BIG>
 __global__ void __launch_bounds__(256)
-word_groups_kernel(const int64_t* __restrict__ gstart, int64_t n_groups, int64_t n_bytes, uint32_t* __restrict__ wg)
+word_groups_kernel(const int64_t* __restrict__ gstart, int64_t n_groups, int64_t n_bytes, uint32_t* __restrict__ wg, uint32_t* __restrict__ big_list,
+                   uint32_t* __restrict__ big_n)
 {
     const int lane = BIG ? threadIdx.x : (threadIdx.x & 31);
     const int step = BIG ? blockDim.x : 32;
     const int64_t first = BIG ? blockIdx.x : (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int64_t stride = BIG ? gridDim.x : (((int64_t)gridDim.x * blockDim.x) >> 5);
-    for (int64_t g = first; g < n_groups; g += stride) {
+    const int64_t n_items = BIG ? (int64_t)*big_n : n_groups;
+    for (int64_t i = first; i < n_items; i += stride) {
+        const int64_t g = BIG ? (int64_t)big_list[i] : i;
         const int64_t lo = __ldg(gstart + g), hi = __ldg(gstart + g + 1);
         if (lo >= hi) continue;
         const int64_t w_first = (lo + 31) >> 5, w_last = (hi - 1) >> 5; // words whose first base lies in [lo, hi)
-        if (((w_last - w_first + 1) > kBigCloudWords) != BIG) continue;
+        if (!BIG && (w_last - w_first + 1) > kBigCloudWords) {
+            if (lane == 0) big_list[atomicAdd(big_n, 1u)] = (uint32_t)g;
+            continue;
+        }
         for (int64_t w = w_first + lane; w <= w_last; w += step) {
             const bool mixed = (w == w_last) && hi < min((w + 1) << 5, n_bytes);
             wg[w] = (uint32_t)g | (mixed ? kWordMixed : 0u);
