@@ -659,6 +659,9 @@ def run_streamed(env):
             z = span()
             spans.append((a, z))
             ctx.synchronize()
+            if os.environ.get("PG_BENCH_DEBUG") == "1":
+                print(f"[bench] count batch {i}: span {a.elapsed_time(z):.1f} ms, driver free {torch.cuda.mem_get_info()[0] / 2**30:.1f} GiB, "
+                      f"torch reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB", file=sys.stderr)
             keep = np.ones(bd["n_groups"], dtype=np.uint8)
             keep[0] = 0  # the cloud that is open when a file starts is labelled "" and dropped (for c4, under the reference's
             # off-by-one, row i then holds pair i + 1: boundary_mode "reference")
@@ -671,12 +674,24 @@ def run_streamed(env):
         rows, abd_sum, tnf_sum, w_sum = 0, 0, 0, 0.0
         z = span()
         spans.append((a, z))
+        debug = os.environ.get("PG_BENCH_DEBUG") == "1"
+        if n_batches > 1:
+            torch.cuda.empty_cache()  # the generator's cached blocks (not part of the path) would crowd the matrices of the featurize pass
         for b, keep, bd in held:
+            if debug:
+                ctx.synchronize()
+                drv_free, drv_total = torch.cuda.mem_get_info()
+                t_host = time.perf_counter()
             a = span()
             f = ctx.featurize(b, keep)
             f.normalize()
             z = span()
             spans.append((a, z))
+            if debug:
+                ctx.synchronize()
+                print(f"[bench] featurize batch: span {a.elapsed_time(z):.1f} ms, host {1e3 * (time.perf_counter() - t_host):.1f} ms, driver free before "
+                      f"{drv_free / 2**30:.1f} GiB, ctx free {ctx.mem_info()[0] / 2**30:.1f} GiB, torch reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB",
+                      file=sys.stderr)
             rows += f.rows
             if collect is not None:  # fold the outputs into a checksum (outside the timed spans)
                 ctx.synchronize()
