@@ -45,8 +45,13 @@ def write_reference_csv(path, names, matrix):
             f.write(str(name) + "," + ",".join(vals) + "\n")
 
 
+def _is_gzip(path):
+    with open(path, "rb") as f:
+        return f.read(2) == b"\x1f\x8b"
+
+
 class Feature:
-    def __init__(self, args, script_path=None, device=0, batch_seq_bytes=None):
+    def __init__(self, args, script_path=None, device=0, batch_seq_bytes=None, ingest=None):
         # /root/reference/src/feature.py:12-26
         self.args = args
         self.tnf_k = str(args.tnf_kmer)
@@ -63,6 +68,12 @@ class Feature:
         # the input is streamed through the GPU in batches of about this many sequence bytes (pangaea_b200/stream.py), so a
         # file of any size works - like the reference, which holds one cloud at a time (count_kmer.cpp:236-282)
         self.batch_seq_bytes = int(batch_seq_bytes or os.environ.get("PG_BATCH_SEQ_BYTES", 0) or stream_mod.DEFAULT_BATCH_SEQ_BYTES)
+        # who parses the text: "device" (pg_ingest_text: the host only moves file bytes - plain-text interleaved input without a
+        # quality filter), "host" (csrc/fastq.cpp: gzip, paired files, the quality filter), "auto" = the device where it applies
+        self.ingest = ingest or os.environ.get("PG_INGEST", "auto")
+        if self.ingest not in ("auto", "device", "host"):
+            raise ValueError("ingest must be auto, device or host")
+        self.ingest_used = None
 
     # -- file names of the reference's cache artefacts (feature.py:42-44,68-71,126-127)
     def _abd_pkl(self):
@@ -98,10 +109,25 @@ class Feature:
             ctx = _lib.Context(device=self.device, k=int(self.kmer), tnf_k=int(self.tnf_k), window_size=int(self.ws),
                                vector_size=int(self.vs), min_length=int(self.minl), min_qual_char=min_qual)
             size = sum(os.path.getsize(p) for p in (path1, path2) if p)
-            hint = None if str(path1).endswith(".gz") else 0.45 * size  # (sequence lines are ~40 % of a plain FASTQ's bytes)
-            names, feats = stream_mod.extract_features_streaming(
-                ctx, lambda: _lib.FastqStream(path1, path2, want_qual=bool(min_qual), pinned=True, target_seq_bytes=self.batch_seq_bytes),
-                seq_bytes_hint=hint)
+            eligible = path2 is None and not min_qual and not _is_gzip(path1)
+            if self.ingest == "device" and not eligible:
+                raise ValueError("the device parser takes one plain-text interleaved file and no quality filter")
+            names = feats = None
+            if eligible and self.ingest != "host":
+                window = int(min(1 << 30, max(1 << 12, self.batch_seq_bytes / 0.45)))  # file bytes per window (~45 % are sequence)
+                try:
+                    names, feats = stream_mod.extract_features_device_ingest(ctx, path1, window_bytes=window)
+                    self.ingest_used = "device"
+                except _lib.PgError as e:
+                    if self.ingest == "device" or e.code not in (-1, -5):  # (PG_ERR_INVALID / PG_ERR_STATE: the text, not the GPU)
+                        raise
+                    logging.info(f"device parser declined the input ({e}); host reader")
+            if feats is None:
+                hint = None if _is_gzip(path1) else 0.45 * size  # (sequence lines are ~40 % of a plain FASTQ's bytes)
+                names, feats = stream_mod.extract_features_streaming(
+                    ctx, lambda: _lib.FastqStream(path1, path2, want_qual=bool(min_qual), pinned=True, target_seq_bytes=self.batch_seq_bytes),
+                    seq_bytes_hint=hint)
+                self.ingest_used = "host"
             names = np.array(names, dtype=object)
             abd32, tnf32 = feats.raw()
             abundance, tnf = abd32.astype(np.int64), tnf32.astype(np.int64)

@@ -87,7 +87,7 @@ class DeviceIngest:
             yield batch, keep, labels, True
             return
         L = _lib.lib()
-        W, slack = self.window, self.slack
+        W, slack = max(1, min(self.window, n)), self.slack  # (a small file: one window of its own size, not a 1 GiB pinned buffer)
         n_win = (n + W - 1) // W
         dev_name = f"cuda:{ctx.params.device}"
         host = [torch.empty(W, dtype=torch.uint8, pin_memory=True) for _ in range(min(2, n_win))]

@@ -406,15 +406,19 @@ def _args(out, **kw):
     return argparse.Namespace(**d)
 
 
-def test_feature_and_data_drop_in(tmp_path, oracle):
+@pytest.mark.parametrize("ingest", ["device", "host"])
+def test_feature_and_data_drop_in(tmp_path, oracle, ingest):
+    """The drop-in classes end to end, with the text parsed on the device (the default for a plain interleaved file) and by
+    the host reader."""
     from pangaea_b200 import Data, Feature
 
     data = synth.generate(n_barcodes=40, mean_pairs=20, read_len=100, n_genomes=3, genome_len=50_000, frag_len=8_000, seed=21,
                           unbarcoded_pairs=4)
     path = synth.write_interleaved(str(tmp_path / "reads.fq"), data)
     names, abd, tnf = oracle.featurize(path, None)
-    ft = Feature(_args(tmp_path, interleaved_reads=path), script_path="unused")
+    ft = Feature(_args(tmp_path, interleaved_reads=path), script_path="unused", ingest=None if ingest == "device" else ingest)
     g_names, g_abd, g_tnf = ft.extract_features(write_csv=True)
+    assert ft.ingest_used == ingest  # ("auto" picks the device parser for this input)
     assert g_abd.dtype == np.int64 and g_abd.shape == abd.shape
     assert list(g_names) == list(names) and np.array_equal(g_abd, abd) and np.array_equal(g_tnf, tnf)
     fd = tmp_path / "1.features"
@@ -709,6 +713,14 @@ def test_feature_streams_gzip_and_paired_input(tmp_path, oracle):
     names, abd, tnf = ft.extract_features(write_cache=False)
     assert list(names) == list(want[0]) and np.array_equal(abd, want[1]) and np.array_equal(tnf, want[2])
     assert ft.features.rows == len(names)  # all batches' rows as one device-resident feature set
+    assert ft.ingest_used == "host"  # gzip: the host reader
+    # the same file as plain text: parsed on the device, in several 44 kB windows
+    ft = Feature(_args(tmp_path / "d", interleaved_reads=g.path1, min_length=g.params["min_length"]), "unused", batch_seq_bytes=20_000)
+    names, abd, tnf = ft.extract_features(write_cache=False)
+    assert ft.ingest_used == "device" and os.path.getsize(g.path1) > 3 * 44_445
+    assert list(names) == list(want[0]) and np.array_equal(abd, want[1]) and np.array_equal(tnf, want[2])
+    with pytest.raises(ValueError):  # the device parser cannot read gzip: asking for it explicitly is an error, not a silent fallback
+        Feature(_args(tmp_path / "e", interleaved_reads=str(gz)), "unused", ingest="device").extract_features(write_cache=False)
 
 
 def test_data_from_device_features_applies_the_csv_rounding(tmp_path, oracle):
