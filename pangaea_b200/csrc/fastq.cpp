@@ -19,6 +19,9 @@
 #include <exception>
 #include <new>
 #include <string>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <thread>
 #include <vector>
 
@@ -118,6 +121,7 @@ void substr(std::string* out, const char* s, size_t len, size_t pos, size_t n)
 
 struct HeaderParser {
     int read_type = 0; // 0 undecided, 1 "10x", 2 "stLFR" - latched once (count_kmer.cpp:24,28-33)
+    // name may be null (interleaved input: only the paired reader compares the names of R1 and R2)
     void parse(const char* line, size_t len, std::string* name, std::string* bc)
     {
         if (read_type == 0) {
@@ -127,14 +131,16 @@ struct HeaderParser {
         if (read_type == 2) { // count_kmer.cpp:36-43
             size_t p1 = find_char(line, len, '#', 0);
             size_t p2 = find_char(line, len, '/', p1 + 1); // npos + 1 == 0, as in the reference
-            substr(name, line, len, 0, p1);
+            if (name) substr(name, line, len, 0, p1);
             substr(bc, line, len, p1 + 1, p2 - p1 - 1);
             if (*bc == "0_0_0") bc->clear();
         } else { // count_kmer.cpp:44-51
-            size_t e = npos;
-            for (size_t i = 0; i < len; ++i)
-                if (line[i] == ' ' || line[i] == '\r' || line[i] == '\t' || line[i] == '\n') { e = i; break; }
-            substr(name, line, len, 0, e);
+            if (name) {
+                size_t e = npos;
+                for (size_t i = 0; i < len; ++i)
+                    if (line[i] == ' ' || line[i] == '\r' || line[i] == '\t' || line[i] == '\n') { e = i; break; }
+                substr(name, line, len, 0, e);
+            }
             bc->clear();
             size_t p1 = find_bxz(line, len);
             if (p1 != npos) {
@@ -325,16 +331,23 @@ void run_threads(int T, Fn&& fn)
     for (auto& e : err) if (e) std::rethrow_exception(e);
 }
 
+// 16 bytes per compare: a match subtracts -1 from its byte lane; the lanes are summed every 255 blocks (psadbw)
 uint64_t count_newlines(const char* p, size_t lo, size_t hi)
 {
     uint64_t c = 0;
-    size_t pos = lo;
-    while (pos < hi) {
-        const char* nl = (const char*)memchr(p + pos, '\n', hi - pos);
-        if (!nl) break;
-        ++c;
-        pos = (size_t)(nl - p) + 1;
+    size_t i = lo;
+#if defined(__SSE2__)
+    const __m128i nl = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+    while (i + 16 <= hi) {
+        __m128i acc = zero;
+        const size_t blocks = std::min<size_t>((hi - i) / 16, 255);
+        for (size_t b = 0; b < blocks; ++b, i += 16)
+            acc = _mm_sub_epi8(acc, _mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(p + i)), nl));
+        const __m128i sums = _mm_sad_epu8(acc, zero);
+        c += (uint64_t)_mm_cvtsi128_si64(sums) + (uint64_t)_mm_cvtsi128_si64(_mm_srli_si128(sums, 8));
     }
+#endif
+    for (; i < hi; ++i) c += p[i] == '\n';
     return c;
 }
 
@@ -350,17 +363,35 @@ uint64_t count_newlines_parallel(const char* p, size_t lo, size_t hi, int T)
     return s;
 }
 
-// calls fn(line_number, ptr, len) for every line of [begin, end); the last line may lack its newline
+// calls fn(line_number, ptr, len) for every line of [begin, end); the last line may lack its newline.
+// FASTQ lines are short (a memchr call per line costs more than the scan itself): 64 bytes per step, the newline positions of
+// the block as a bit mask, one callback per set bit.
 template <class Fn>
 void for_lines(const char* p, size_t begin, size_t end, uint64_t line0, Fn&& fn)
 {
     uint64_t n = line0;
-    size_t pos = begin;
-    while (pos < end) {
-        const char* nl = (const char*)memchr(p + pos, '\n', end - pos);
-        const size_t len = nl ? (size_t)(nl - (p + pos)) : end - pos;
-        fn(n++, p + pos, len);
-        pos += len + 1;
+    size_t start = begin; // first byte of the line being scanned
+    size_t pos = begin;   // no newline in [start, pos)
+#if defined(__SSE2__)
+    const __m128i nl = _mm_set1_epi8('\n');
+    auto mask16 = [&](size_t at) { return (uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(p + at)), nl)); };
+    while (pos + 64 <= end) {
+        uint64_t m = mask16(pos) | (mask16(pos + 16) << 16) | (mask16(pos + 32) << 32) | (mask16(pos + 48) << 48);
+        while (m) {
+            const size_t e = pos + (size_t)__builtin_ctzll(m);
+            fn(n++, p + start, e - start);
+            start = e + 1;
+            m &= m - 1;
+        }
+        pos += 64;
+    }
+#endif
+    while (start < end) {
+        const size_t from = pos > start ? pos : start;
+        const char* q = from < end ? (const char*)memchr(p + from, '\n', end - from) : nullptr;
+        const size_t e = q ? (size_t)(q - p) : end;
+        fn(n++, p + start, e - start);
+        start = pos = e + 1;
     }
 }
 
@@ -537,7 +568,7 @@ void parse_records_parallel(pg_fastq_stream* s, pg_fastq* fq, size_t begin, size
         Piece& pc = pieces[(size_t)t];
         HeaderParser hp;
         hp.read_type = read_type;
-        std::string name, bc, lastp;
+        std::string bc, lastp;
         bool have_last = false;
         size_t so = seq_off[(size_t)t];
         int64_t r = (int64_t)read_off[(size_t)t];
@@ -560,8 +591,8 @@ void parse_records_parallel(pg_fastq_stream* s, pg_fastq* fq, size_t begin, size
         for_lines(p, pc.begin, pc.end, pc.line0, [&](uint64_t ln, const char* sp, size_t len) {
             switch ((ln + 1) % 8) {
             case 1:
-                if (ln < latch_line) { HeaderParser undecided; undecided.parse(sp, len, &name, &bc); }
-                else hp.parse(sp, len, &name, &bc);
+                if (ln < latch_line) { HeaderParser undecided; undecided.parse(sp, len, nullptr, &bc); }
+                else hp.parse(sp, len, nullptr, &bc);
                 break;
             case 2: s1 = so; l1 = len; q1 = true; add_read(sp, len); break;
             case 4: if (q1) set_qual(s1, l1, sp, len); q1 = false; break;
