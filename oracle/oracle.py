@@ -262,15 +262,29 @@ def _read_csv(path):
     return df[0].to_numpy(), df.drop(columns=0).to_numpy()
 
 
-def ref_count_tnf(out_gz, interleaved=None, reads1=None, reads2=None, k=4, mlen=2000, threads=4):
+def _read_csv_raw(path):
+    """The tool's output as it wrote it: rows end with "\\n" only, the label is everything before the first comma.  (pandas
+    also breaks rows at a bare "\\r": a label that carries one - a CRLF header whose label runs to the end of the line -
+    garbles the reference's own read-back, feature.py:115; the differential tests on hostile text compare what the binary
+    wrote.)"""
+    text = gzip.open(path, "rb").read()
+    if not text:
+        return np.array([], dtype=object), None
+    rows = [r for r in text.split(b"\n") if r]
+    labels = np.array([r.split(b",", 1)[0].decode("utf-8", "surrogateescape") for r in rows], dtype=object)
+    vals = np.array([[float(x) for x in r.split(b",")[1:]] for r in rows])
+    return labels, vals
+
+
+def ref_count_tnf(out_gz, interleaved=None, reads1=None, reads2=None, k=4, mlen=2000, threads=4, raw=False):
     cmd = [REF_COUNT_TNF, "-k", str(k), "-t", str(threads), "-l", str(mlen), "-o", out_gz]
     cmd += ["-i", interleaved] if interleaved else ["-1", reads1, "-2", reads2]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
-    return _read_csv(out_gz)
+    return _read_csv_raw(out_gz) if raw else _read_csv(out_gz)
 
 
-def ref_count_kmer(out_gz, dump, interleaved=None, reads1=None, reads2=None, k=15, mlen=2000, vs=400, ws=10, threads=4):
+def ref_count_kmer(out_gz, dump, interleaved=None, reads1=None, reads2=None, k=15, mlen=2000, vs=400, ws=10, threads=4, raw=False):
     cmd = [REF_COUNT_KMER, "-t", str(threads), "-g", dump, "-k", str(k), "-l", str(mlen), "-w", str(ws), "-v", str(vs), "-o", out_gz]
     cmd += ["-i", interleaved] if interleaved else ["-1", reads1, "-2", reads2]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
-    return _read_csv(out_gz)
+    return _read_csv_raw(out_gz) if raw else _read_csv(out_gz)

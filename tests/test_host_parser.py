@@ -394,3 +394,22 @@ def test_streamed_batches_give_the_reference_rows(tmp_path, oracle, golden, targ
     assert names == list(golden.abd_labels) == list(golden.tnf_labels)
     if names:
         assert np.array_equal(np.concatenate(abd), golden.abd) and np.array_equal(np.concatenate(tnf), golden.tnf)
+
+
+@pytest.mark.parametrize("seed", range(100, 108))
+def test_host_reader_on_hostile_headers_matches_the_oracle(tmp_path, oracle, seed):
+    """The hostile interleaved texts of tests/test_oracle_vs_ref.py (where the oracle is checked against the reference binaries):
+    host reader -> batch contract evaluated in Python == oracle.  Labels with a trailing '\\r' included."""
+    from test_oracle_vs_ref import _hostile_text
+
+    path = str(tmp_path / "h.fq")
+    open(path, "wb").write(_hostile_text(seed))
+    k, tnf_k, mlen, vs, ws = 9, 3, 30, 11, 2
+    table = oracle.count_fastq([path], k)
+    want_names, want_abd, want_tnf = oracle.featurize(path, None, k=k, tnf_k=tnf_k, mlen=mlen, vs=vs, ws=ws, table=table)
+    fq = _lib.Fastq(path)
+    seq, off, flag, keep = fq.arrays()
+    labels = [fq.label(g) for g in range(fq.n_groups)]
+    names, abd, tnf = contract_features(seq, off, flag, keep, labels, table, k, tnf_k, mlen, vs, ws)
+    assert names == list(want_names)
+    assert len(names) == 0 or (np.array_equal(abd, want_abd) and np.array_equal(tnf, want_tnf))

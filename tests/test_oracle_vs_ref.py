@@ -81,3 +81,80 @@ def test_kat5_csv_precision_loss_is_text_only(ref, tmp_path):
     rl, rt = ref.ref_count_tnf(str(tmp_path / "t.gz"), interleaved=fq, mlen=0)
     assert rt.dtype == np.float64  # pandas sees scientific notation
     assert rt[0, 0] == float("%.6g" % exact) and rt[0, 0] != exact
+
+
+def _hostile_text(seed):
+    """Interleaved FASTQ text built from the header spellings getBarcode (count_kmer.cpp:25-53) has to cope with: BX tags with
+    and without the "-1" suffix, behind a tab or a blank, in the middle of other tags, missing; stLFR '#' labels with and
+    without the "/1" suffix, the 0_0_0 label, a second '#'; both kinds in one file (the first decisive header latches the type);
+    reads shorter than k, empty reads, CRLF, N / lower case / other bytes; sometimes a truncated last record."""
+    rng = np.random.default_rng(seed)
+    n_clouds = int(rng.integers(2, 12))
+    first_kind = "10x" if rng.random() < 0.5 else "stlfr"
+    recs = []
+    rid = 0
+    for c in range(n_clouds):
+        bc10 = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(rng.integers(1, 17))))
+        bcst = b"%d_%d_%d" % tuple(int(x) for x in rng.integers(0 if rng.random() < 0.15 else 1, 1500, size=3))
+        if rng.random() < 0.1:
+            bcst = b"0_0_0"
+        for _ in range(int(rng.integers(1, 9))):
+            kind = first_kind if (c == 0 or rng.random() < 0.85) else ("stlfr" if first_kind == "10x" else "10x")
+            r = rng.random()
+            if kind == "10x":
+                sep = b"\t" if rng.random() < 0.5 else b" "
+                if r < 0.55:
+                    tag = sep + b"BX:Z:" + bc10 + b"-1"
+                elif r < 0.7:
+                    tag = sep + b"BX:Z:" + bc10
+                elif r < 0.85:
+                    tag = sep + b"RX:Z:NNN" + sep + b"BX:Z:" + bc10 + b"-1" + sep + b"QX:Z:III"
+                else:
+                    tag = b""
+                head = b"@r%d" % rid + tag
+            else:
+                if r < 0.6:
+                    head = b"@r%d#" % rid + bcst + b"/%d"
+                elif r < 0.8:
+                    head = b"@r%d#" % rid + bcst
+                elif r < 0.9:
+                    head = b"@r#%d#" % rid + bcst + b"/%d"
+                else:
+                    head = b"@r%d" % rid
+            eol = b"\r\n" if rng.random() < 0.05 else b"\n"
+            for mate in (1, 2):
+                L = int(rng.choice([0, 3, 9, 14, 15, 16, 40, 100, 151]))
+                s = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L).tobytes())
+                for _ in range(int(rng.integers(0, 3))):
+                    if L:
+                        s[int(rng.integers(0, L))] = int(rng.choice(np.frombuffer(b"Nacgt.R", np.uint8)))
+                h = head % mate if b"%d" in head else head
+                recs.append(h + eol + bytes(s) + eol + b"+" + eol + b"I" * L + eol)
+            rid += 1
+    if rng.random() < 0.3:
+        recs.append(b"@tail\tBX:Z:ACGT-1\nACGTACGTACGTACGTACGT\n")  # truncated: R1 sequence only
+    return b"".join(recs)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_hostile_headers_and_ragged_reads(ref, tmp_path, seed):
+    """The restatement against the reference binaries on hostile interleaved text (labels, grouping off-by-one, the latch,
+    min-length with separators, short / empty / dirty reads)."""
+    O = ref
+    rng = np.random.default_rng(seed)
+    path = str(tmp_path / "h.fq")
+    open(path, "wb").write(_hostile_text(seed))
+    k, ws, vs = int(rng.choice([5, 9, 15])), int(rng.integers(1, 4)), int(rng.integers(3, 30))
+    mlen = int(rng.choice([0, 30, 300]))
+    t = O.count_fastq([path], k)
+    dump = str(tmp_path / "d.dump")
+    t.write_dump(dump, k)
+    labels, abd = O.abundance(path, None, t, k, mlen, vs, ws)
+    rl, rabd = O.ref_count_kmer(str(tmp_path / "a.gz"), dump, k=k, mlen=mlen, vs=vs, ws=ws, interleaved=path, raw=True)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(abd, rabd)
+    tk = int(rng.choice([3, 4]))
+    labels, tnf = O.tnf(path, None, tk, mlen)
+    rl, rtnf = O.ref_count_tnf(str(tmp_path / "t.gz"), k=tk, mlen=mlen, interleaved=path, raw=True)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(tnf, rtnf)
