@@ -413,3 +413,20 @@ def test_host_reader_on_hostile_headers_matches_the_oracle(tmp_path, oracle, see
     names, abd, tnf = contract_features(seq, off, flag, keep, labels, table, k, tnf_k, mlen, vs, ws)
     assert names == list(want_names)
     assert len(names) == 0 or (np.array_equal(abd, want_abd) and np.array_equal(tnf, want_tnf))
+
+
+@pytest.mark.parametrize("seed", range(200, 206))
+def test_host_reader_on_hostile_paired_files_matches_the_oracle(tmp_path, oracle, seed):
+    """Paired files whose mates sometimes disagree in name or barcode (PG_READ_NOFEAT: counted, in no cloud)."""
+    from test_oracle_vs_ref import _hostile_pair_files
+
+    p1, p2 = _hostile_pair_files(seed, tmp_path)
+    k, tnf_k, mlen, vs, ws = 9, 3, 30, 11, 2
+    table = oracle.count_fastq([p1, p2], k)
+    want_names, want_abd, want_tnf = oracle.featurize(p1, p2, k=k, tnf_k=tnf_k, mlen=mlen, vs=vs, ws=ws, table=table)
+    fq = _lib.Fastq(p1, p2)
+    seq, off, flag, keep = fq.arrays()
+    labels = [fq.label(g) for g in range(fq.n_groups)]
+    names, abd, tnf = contract_features(seq, off, flag, keep, labels, table, k, tnf_k, mlen, vs, ws)
+    assert names == list(want_names)
+    assert len(names) == 0 or (np.array_equal(abd, want_abd) and np.array_equal(tnf, want_tnf))

@@ -158,3 +158,49 @@ def test_hostile_headers_and_ragged_reads(ref, tmp_path, seed):
     rl, rtnf = O.ref_count_tnf(str(tmp_path / "t.gz"), k=tk, mlen=mlen, interleaved=path, raw=True)
     assert list(labels) == list(rl)
     assert len(rl) == 0 or np.array_equal(tnf, rtnf)
+
+
+def _hostile_pair_files(seed, tmp_path):
+    rng = np.random.default_rng(seed + 7)
+    text = _hostile_text(seed).replace(b"\r\n", b"\n")
+    lines = text.split(b"\n")
+    recs = [lines[i:i + 4] for i in range(0, len(lines) - 3, 4)]
+    recs = recs[: len(recs) // 2 * 2]
+    r1, r2 = [], []
+    for i in range(0, len(recs), 2):
+        a, b = list(recs[i]), list(recs[i + 1])
+        u = rng.random()
+        if u < 0.12:
+            b[0] = b[0].replace(b"@r", b"@x", 1)                      # another read name
+        elif u < 0.24:
+            b[0] = b[0].replace(b"BX:Z:", b"BX:Z:T").replace(b"#", b"#9", 1)  # another barcode
+        elif u < 0.30:
+            b[0] = b[0].split(b"\t")[0].split(b" ")[0].split(b"#")[0]  # no barcode at all
+        r1.append(b"\n".join(a) + b"\n")
+        r2.append(b"\n".join(b) + b"\n")
+    p1, p2 = str(tmp_path / "1.fq"), str(tmp_path / "2.fq")
+    open(p1, "wb").write(b"".join(r1))
+    open(p2, "wb").write(b"".join(r2))
+    return p1, p2
+
+
+@pytest.mark.parametrize("seed", range(200, 208))
+def test_hostile_paired_files(ref, tmp_path, seed):
+    """Paired mode (count_kmer.cpp:181-235): the hostile records dealt to two files, then some R2 headers changed - another
+    read name, another barcode, no barcode - so that pairs disagree (they are k-mer counted but belong to no cloud)."""
+    O = ref
+    rng = np.random.default_rng(seed)
+    p1, p2 = _hostile_pair_files(seed, tmp_path)
+    k, ws, vs = int(rng.choice([5, 9, 15])), int(rng.integers(1, 4)), int(rng.integers(3, 30))
+    mlen = int(rng.choice([0, 30, 300]))
+    t = O.count_fastq([p1, p2], k)
+    dump = str(tmp_path / "d.dump")
+    t.write_dump(dump, k)
+    labels, abd = O.abundance(p1, p2, t, k, mlen, vs, ws)
+    rl, rabd = O.ref_count_kmer(str(tmp_path / "a.gz"), dump, k=k, mlen=mlen, vs=vs, ws=ws, reads1=p1, reads2=p2, raw=True)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(abd, rabd)
+    labels, tnf = O.tnf(p1, p2, 4, mlen)
+    rl, rtnf = O.ref_count_tnf(str(tmp_path / "t.gz"), k=4, mlen=mlen, reads1=p1, reads2=p2, raw=True)
+    assert list(labels) == list(rl)
+    assert len(rl) == 0 or np.array_equal(tnf, rtnf)
