@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import ctypes as C
 import gzip
-import os
 
 import numpy as np
 
