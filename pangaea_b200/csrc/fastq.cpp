@@ -18,6 +18,7 @@
 #include <cstring>
 #include <exception>
 #include <new>
+#include <future>
 #include <string>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -37,32 +38,56 @@ namespace {
 
 struct LineReader {
     gzFile f = nullptr;
-    std::vector<char> buf;
+    std::vector<char> bufs[2];   // one is parsed while a helper thread inflates / reads the next 16 MB into the other
+    int cur = 0;
     size_t pos = 0, end = 0;
     bool eof = false;
     bool failed = false; // a read error or a truncated gzip stream: the caller must not take what came so far for the file
     std::string spill; // a line that straddles two chunks
+    struct Fill { int n; int errnum; };
+    std::future<Fill> pending;   // the read-ahead of bufs[cur ^ 1] (of bufs[0] before the first fill)
+    int pending_buf = 0;
 
+    Fill read_into(int b)
+    {
+        Fill r;
+        r.n = gzread(f, bufs[b].data(), (unsigned)bufs[b].size());
+        r.errnum = Z_OK;
+        if (r.n <= 0) gzerror(f, &r.errnum); // Z_BUF_ERROR: the compressed stream ends early
+        return r;
+    }
+    void read_ahead(int b)
+    {
+        pending_buf = b;
+        pending = std::async(std::launch::async, [this, b]() { return read_into(b); });
+    }
     bool open(const char* path)
     {
         f = gzopen(path, "rb"); // transparent for plain text, like the reference's igzstream
         if (!f) return false;
         gzbuffer(f, 1 << 22);
-        buf.resize(1 << 24);
+        bufs[0].resize(1 << 24);
+        bufs[1].resize(1 << 24);
+        read_ahead(0); // (with two files their first chunks inflate side by side)
         return true;
     }
-    ~LineReader() { if (f) gzclose(f); }
+    ~LineReader()
+    {
+        if (pending.valid()) pending.wait(); // the helper still holds the gzFile
+        if (f) gzclose(f);
+    }
     bool fill()
     {
         if (eof) return false;
-        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        const Fill r = pending.get();
+        cur = pending_buf;
         pos = 0;
-        end = n > 0 ? (size_t)n : 0;
-        if (n <= 0) {
+        end = r.n > 0 ? (size_t)r.n : 0;
+        if (r.n <= 0) {
             eof = true;
-            int errnum = Z_OK;
-            gzerror(f, &errnum); // Z_BUF_ERROR: the compressed stream ends early
-            if (n < 0 || (errnum != Z_OK && errnum != Z_STREAM_END)) failed = true;
+            if (r.n < 0 || (r.errnum != Z_OK && r.errnum != Z_STREAM_END)) failed = true;
+        } else {
+            read_ahead(cur ^ 1);
         }
         return end > 0;
     }
@@ -74,7 +99,7 @@ struct LineReader {
         bool have = false;
         for (;;) {
             if (pos == end && !fill()) break;
-            const char* s = buf.data() + pos;
+            const char* s = bufs[cur].data() + pos;
             const char* nl = (const char*)memchr(s, '\n', end - pos);
             if (nl) {
                 size_t n = (size_t)(nl - s);
